@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the MSDeformAttn hot path (BASELINE.json config 2) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--dist init|trained|adversarial]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + one backward of the op on one batch of synthetic input:
+B = 8 images of 1024x1024 per GPU (levels 32^2 / 64^2 / 128^2, S = Q = 21504, H = 8, D = 32, L = 3,
+P = 4), bf16 values/weights, fp32 locations -- the configuration BASELINE.json's metric is quoted on.
+Ranks work on independent batches (the path shards by image; no data-path collective), so scaling
+is weak and `value` = images all ranks processed / max-over-ranks device time.
+
+Output: ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every key).
+`--impl reference` times the reference's own implementation (HF `multi_scale_deformable_attention`,
+M2F:798-837, fp32, autograd backward) on the host CPU with all threads, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPES_C2 = [(32, 32), (64, 64), (128, 128)]
+B_PER_GPU = 8
+H, D, L, P = 8, 32, 3, 4
+METRIC = "msda_fwd_bwd_throughput"
+UNIT = "images/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--dist", choices=["init", "trained", "adversarial"], default="init")
+    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other location distributions and fp32")
+    return ap.parse_args()
+
+
+def algorithmic_bytes(B, S, dtype):
+    """compulsory traffic, Q == S, H=8 D=32 L=3 P=4."""
+    fwd, bwd = (1984, 3456) if dtype == "bf16" else (3200, 5376)
+    return fwd * B * S, bwd * B * S
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture, if one has been recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop = [], set(), threading.Event()
+        self.max_mhz, self.thread = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        if self.thread is not None:
+            self.thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def reference_step_fn(n_images, q_fraction=1.0):
+    """One fwd+bwd of the reference implementation on the CPU (fp32, autograd), as a closure."""
+    import torch
+    from oracle.hf_reference import hf_forward_torch
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    x = msda_inputs(n_images, SHAPES_C2, num_heads=H, head_dim=D, num_points=P, dist="init", seed=0)
+    nq = max(1, int(round(x["sampling_locations"].shape[1] * q_fraction)))
+    v = x["value"].requires_grad_(True)
+    lo = x["sampling_locations"][:, :nq].contiguous().requires_grad_(True)
+    a = x["attention_weights"][:, :nq].contiguous().requires_grad_(True)
+    go = x["grad_out"][:, :nq].contiguous()
+
+    def step():
+        v.grad = lo.grad = a.grad = None
+        out = hf_forward_torch(v, SHAPES_C2, lo, a)
+        out.backward(go)
+        return out
+
+    return step, nq
+
+
+def run_reference(args, rank, world):
+    import torch
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, nq = reference_step_fn(1)
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    # keep the whole run within a few minutes: shrink the query sample if K steps would not fit
+    budget = 150.0
+    frac = 1.0
+    total = (args.steps + args.warmup) * t1
+    if total > budget:
+        frac = max(1.0 / 16.0, budget / total)
+        step, nq = reference_step_fn(1, frac)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    S = sum(h * w for h, w in SHAPES_C2)
+    images = nq / S
+    value = images / dt
+    sample = f"1 image (B=1 of the B=8 batch), {nq} of {S} queries per step, fp32, autograd backward"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config("init", "fp32"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(dist, dtype):
+    return {
+        "workload": "BASELINE.json configs[1]: MSDeformAttn fwd+bwd op microbench, batch 8 per GPU, 1024x1024 input "
+                    "(levels 32^2/64^2/128^2, S=Q=21504), H=8 D=32 L=3 P=4",
+        "batch_per_gpu": B_PER_GPU, "spatial_shapes": SHAPES_C2, "locations": dist,
+        "contract": "value/out/grads bf16, sampling_locations fp32, attention_weights bf16, fp32 accumulate"
+        if dtype == "bf16" else "all fp32",
+        "l2": "no flush: each step touches ~0.9 GB (> 126 MB L2), inputs 341 MB",
+    }
+
+
+# --------------------------------------------------------------------------------------------- b200 arm
+class Problem:
+    """Device buffers + descriptor for direct C-ABI calls (no autograd in the timed region)."""
+
+    def __init__(self, dist, dtype, device, seed):
+        import torch
+        from weed_instance_segmentation_b200 import _cabi, functional
+        from weed_instance_segmentation_b200.synth import msda_inputs
+        self.torch, self.cabi = torch, _cabi
+        self.lib = _cabi.load()
+        tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+        x = msda_inputs(B_PER_GPU, SHAPES_C2, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=seed,
+                        device=device, value_dtype=tdt)
+        self.x = x
+        self.value, self.loc, self.attn, self.go = (x["value"], x["sampling_locations"], x["attention_weights"],
+                                                    x["grad_out"])
+        self.S = self.value.shape[1]
+        self.out = torch.empty_like(self.go)
+        self.gv, self.gl, self.ga = torch.empty_like(self.value), torch.empty_like(self.loc), torch.empty_like(self.attn)
+        code = _cabi.BF16 if dtype == "bf16" else _cabi.F32
+        lsi = x["level_start_index"].tolist()
+        self.order = functional.query_order_2d(SHAPES_C2, functional._TILE, device) if functional._USE_ORDER else None
+        self.flags = _cabi.FLAG_BF16_ATOMICS if (functional._BF16_ATOMICS and dtype == "bf16") else 0
+        self.desc, self._keep = _cabi.make_desc(B_PER_GPU, self.S, self.S, H, D, L, P, code, code, SHAPES_C2, lsi, self.flags)
+        self.pdesc, self._keep2 = _cabi.make_desc(B_PER_GPU, self.S, self.S, H, D, L, P, code, code, SHAPES_C2, lsi,
+                                                  self.flags | _cabi.FLAG_PROFILE)
+        nws = int(self.lib.msda_b200_backward_workspace_bytes(self.desc))
+        self.ws = torch.empty(nws, dtype=torch.uint8, device=device) if nws else None
+        self.nws = nws
+        self.stream = torch.cuda.current_stream().cuda_stream
+
+    def _p(self, t):
+        return t.data_ptr() if t is not None else None
+
+    def fwd(self, desc=None):
+        self.cabi.check(self.lib.msda_b200_forward(desc or self.desc, self._p(self.value), self._p(self.loc),
+                                                   self._p(self.attn), self._p(self.out), self._p(self.order), self.stream))
+
+    def bwd(self, desc=None):
+        self.cabi.check(self.lib.msda_b200_backward(desc or self.desc, self._p(self.value), self._p(self.loc),
+                                                    self._p(self.attn), self._p(self.go), self._p(self.gv), self._p(self.gl),
+                                                    self._p(self.ga), self._p(self.ws), self.nws, self._p(self.order),
+                                                    self.stream))
+
+    def step(self):
+        self.fwd()
+        self.bwd()
+
+
+def time_steps(torch, fn, steps, warmup, barrier):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3  # seconds for K steps
+
+
+def profile_kernels(prob, iters):
+    """Per-kernel device time from events the library records around each launch."""
+    c = prob.cabi
+    acc = {"fwd": [], "bwd_zero": [], "bwd_main": [], "bwd_convert": []}
+    for _ in range(iters):
+        prob.fwd(prob.pdesc)
+        prob.bwd(prob.pdesc)
+        prob.torch.cuda.synchronize()
+        acc["fwd"].append(c.profile_ms(c.PROF_FWD))
+        acc["bwd_zero"].append(c.profile_ms(c.PROF_BWD_ZERO))
+        acc["bwd_main"].append(c.profile_ms(c.PROF_BWD_MAIN))
+        if prob.nws:
+            acc["bwd_convert"].append(c.profile_ms(c.PROF_BWD_CONVERT))
+    return {k: (sum(v) / len(v) if v else 0.0) for k, v in acc.items()}
+
+
+def e2e_steps(torch, wis, prob, steps, warmup, barrier):
+    """Same op through the public Python API with HOST (pinned) buffers: H2D of the step's inputs and D2H of its
+    results inside the timed region."""
+    host_in = [t.detach().cpu().pin_memory() for t in (prob.value, prob.loc, prob.attn, prob.go)]
+    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    host_out = None
+    lsi = prob.x["level_start_index"]
+
+    def step():
+        nonlocal host_out
+        v, lo, a, go = (t.to("cuda", non_blocking=True) for t in host_in)
+        v.requires_grad_(True), lo.requires_grad_(True), a.requires_grad_(True)
+        out = wis.ms_deform_attn(v, SHAPES_C2, lsi, lo, a)
+        out.backward(go)
+        res = (out.detach(), v.grad, lo.grad, a.grad)
+        if host_out is None:
+            host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res]
+        for h, t in zip(host_out, res):
+            h.copy_(t, non_blocking=True)
+
+    secs = time_steps(torch, step, steps, warmup, barrier)
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    return secs, h2d, d2h
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import weed_instance_segmentation_b200 as wis
+    from weed_instance_segmentation_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    prob = Problem(args.dist, args.dtype, device, seed=rank)
+    S = prob.S
+    _cabi.launch_count(reset=True)
+    with ClockSampler(local_rank) as clocks:
+        secs = max_over_ranks(time_steps(torch, prob.step, args.steps, args.warmup, barrier))
+    launches = _cabi.launch_count() // max(args.steps + args.warmup, 1)
+    ms_step = secs / args.steps * 1e3
+    value = world * B_PER_GPU * args.steps / secs
+
+    # per-kernel times (library-recorded events), fwd-only and bwd-only call times
+    kern = profile_kernels(prob, min(args.steps, 20))
+    fwd_ms = time_steps(torch, prob.fwd, args.steps, 3, barrier) / args.steps * 1e3
+    bwd_ms = time_steps(torch, prob.bwd, args.steps, 3, barrier) / args.steps * 1e3
+
+    peak, peak_src = measured_peak_gbs()
+    ab_fwd, ab_bwd = algorithmic_bytes(B_PER_GPU, S, args.dtype)
+    dominant = "bwd_main" if kern["bwd_main"] >= kern["fwd"] else "fwd"
+    dom_bytes = ab_bwd if dominant == "bwd_main" else ab_fwd
+    dom_ms = kern[dominant]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "msda_bwd_kernel" if dominant == "bwd_main" else "msda_fwd_kernel",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms, "traffic": recorded_traffic(dominant),
+    }
+    step_achieved = (ab_fwd + ab_bwd) / (ms_step * 1e-3) / 1e9
+    roofline_step = {
+        "what": "whole fwd+bwd step (forward kernel + zero-fill + backward kernel + bf16 convert)",
+        "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+        "algorithmic_bytes": ab_fwd + ab_bwd,
+        "fwd": {"ms": fwd_ms, "frac": ab_fwd / (fwd_ms * 1e-3) / 1e9 / peak},
+        "bwd": {"ms": bwd_ms, "frac": ab_bwd / (bwd_ms * 1e-3) / 1e9 / peak},
+        "kernels_ms": kern,
+    }
+
+    # end to end through the public API with host buffers
+    e2e_k = max(3, min(args.steps, 10))
+    e2e_secs, h2d, d2h = e2e_steps(torch, wis, prob, e2e_k, 3, barrier)
+    e2e_secs = max_over_ranks(e2e_secs)
+    e2e = {"value": world * B_PER_GPU * e2e_k / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_k, "ms_per_step": e2e_secs / e2e_k * 1e3,
+           "api": "weed_instance_segmentation_b200.ms_deform_attn + autograd backward, pinned host buffers"}
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        for dname, dt in (("init", "bf16"), ("trained", "bf16"), ("adversarial", "bf16"), ("init", "fp32")):
+            if (dname, dt) == (args.dist, args.dtype):
+                continue
+            p2 = Problem(dname, dt, device, seed=rank)
+            s2 = time_steps(torch, p2.step, max(10, args.steps // 4), 3, barrier) / max(10, args.steps // 4)
+            f2, b2 = algorithmic_bytes(B_PER_GPU, S, dt)
+            extras[f"{dname}/{dt}"] = {"ms_per_step": s2 * 1e3, "images_per_s": B_PER_GPU / s2,
+                                       "frac_of_hbm_peak": (f2 + b2) / s2 / 1e9 / peak}
+            del p2
+            torch.cuda.empty_cache()
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        step, nq = reference_step_fn(1)
+        step()  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 20):
+            step()
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": f"{n} fwd+bwd steps of 1 image (B=1 of the B=8 batch, all {nq} queries), reference "
+                                  f"HF function M2F:798-837 in fp32 with autograd, {dt * 1e3:.0f} ms per image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args.dist, args.dtype),
+            "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+            "clocks": clocks.summary(), "other_workloads": extras,
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

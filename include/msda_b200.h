@@ -1,0 +1,132 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention library
+ * (libmsda_b200.so, built from weed_instance_segmentation_b200/csrc/).
+ *
+ * This is the drop-in boundary for the one hot path this repository accelerates:
+ * the pixel-decoder multi-scale deformable attention of the Mask2Former model that
+ * marco-conciatori-public/weed_instance_segmentation fine-tunes.  The reference has no
+ * FFI of its own; the interface each entry point replaces is the Python function
+ *
+ *   transformers/models/mask2former/modeling_mask2former.py:798-837   (M2F:798)
+ *     multi_scale_deformable_attention(value, value_spatial_shapes,
+ *                                      sampling_locations, attention_weights)
+ *
+ * called from M2F:980 by every pixel-decoder encoder layer and reached from the
+ * reference at models/mask2former/train.py:196 (train), train.py:28 (validation),
+ * models/metrics.py:56 and models/mask2former/inference.py:27.  The five-tensor
+ * argument order (value, value_spatial_shapes, level_start_index, sampling_locations,
+ * attention_weights) is the original Deformable-DETR operator order that
+ * transformers/models/deformable_detr/modeling_deformable_detr.py:171-181 keeps.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch types.  Every `dev` pointer is CUDA device
+ *     memory on the current device, every `host` pointer is ordinary host memory.
+ *   - All tensors are contiguous, C order:
+ *       value  (B, S, H, D)         dtype = value_dtype
+ *       loc    (B, Q, H, L, P, 2)   float32 always, last dim (x, y), normalised to [0,1]
+ *       attn   (B, Q, H, L, P)      dtype = attn_dtype (post-softmax weights)
+ *       out    (B, Q, H*D)          dtype = value_dtype, channel index h*D + d
+ *     Level l occupies rows [level_start_index[l], + H_l*W_l) of S, row-major y*W_l + x.
+ *   - The library borrows the pointers for the duration of the call's enqueued work,
+ *     allocates nothing persistent on the device, holds no global mutable state besides
+ *     a thread-local error string and optional profiling events, and launches on the
+ *     stream given (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Return value: 0 on success, otherwise one of MSDA_B200_ERR_*; the message is
+ *     available from msda_b200_last_error() on the calling thread.  Nothing throws.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+#define MSDA_B200_MAX_LEVELS 8
+
+/* dtype codes */
+#define MSDA_B200_F32 0
+#define MSDA_B200_BF16 1
+
+/* error codes */
+#define MSDA_B200_OK 0
+#define MSDA_B200_ERR_INVALID 1     /* null pointer, negative size, level table outside S ...   */
+#define MSDA_B200_ERR_UNSUPPORTED 2 /* head dim / dtype combination without a kernel            */
+#define MSDA_B200_ERR_CUDA 3        /* a CUDA runtime call or launch failed                      */
+#define MSDA_B200_ERR_WORKSPACE 4   /* workspace missing or smaller than ..._workspace_bytes()   */
+
+/* flags (msda_b200_desc.flags) */
+#define MSDA_B200_FLAG_PROFILE 1u        /* record CUDA events around each kernel (see below)    */
+#define MSDA_B200_FLAG_BF16_ATOMICS 2u   /* backward, bf16: accumulate grad_value with packed    */
+                                         /* bf16x2 atomics in place (no fp32 workspace, lossy)   */
+
+/* Problem description: plain old data, filled by the caller on the host. */
+typedef struct msda_b200_desc {
+  int32_t B;           /* batch                                                                  */
+  int32_t S;           /* value rows = sum_l H_l*W_l (may be larger than the sum)                */
+  int32_t Q;           /* queries                                                                */
+  int32_t H;           /* heads                                                                  */
+  int32_t D;           /* channels per head: 8, 16, 32, 64, 128                                  */
+  int32_t L;           /* levels, 1..MSDA_B200_MAX_LEVELS                                        */
+  int32_t P;           /* points per level                                                       */
+  int32_t value_dtype; /* MSDA_B200_F32 | MSDA_B200_BF16: value, out, grad_out, grad_value       */
+  int32_t attn_dtype;  /* MSDA_B200_F32 | MSDA_B200_BF16: attn, grad_attn                        */
+  uint32_t flags;      /* MSDA_B200_FLAG_*                                                       */
+  const int32_t* spatial_shapes_hw;  /* host, L x 2 = (H_l, W_l); M2F:1312 spatial_shapes_list   */
+  const int64_t* level_start_index;  /* host, L; M2F:1321                                        */
+} msda_b200_desc;
+
+/* ABI version of the loaded library (== MSDA_B200_ABI_VERSION it was built with). */
+int msda_b200_abi_version(void);
+
+/* Message of the last failure on this thread ("" if none). Never NULL. */
+const char* msda_b200_last_error(void);
+
+/*
+ * Forward.  Replaces M2F:798-837.
+ *   out[b,q,h*D+d] = sum_{l,p} attn[b,q,h,l,p] * bilinear(value_l[b,:,h,d]; x = loc_x*W_l - 0.5,
+ *                                                         y = loc_y*H_l - 0.5), zeros outside.
+ * query_order (dev, optional, Q int32): a permutation of 0..Q-1 giving the order in which
+ * queries are assigned to thread blocks (scheduling only; results do not depend on it).
+ */
+int msda_b200_forward(const msda_b200_desc* desc, const void* value /*dev*/, const float* loc /*dev*/,
+                      const void* attn /*dev*/, void* out /*dev*/, const int32_t* query_order /*dev|NULL*/,
+                      void* stream);
+
+/* Bytes of device scratch msda_b200_backward needs for this problem (0 if none). */
+size_t msda_b200_backward_workspace_bytes(const msda_b200_desc* desc);
+
+/*
+ * Backward.  Replaces autograd through M2F:798-837 (grid_sampler_2d_backward x L, etc.).
+ * Writes every element of grad_value (B,S,H,D; the library zero-fills it first),
+ * grad_loc (B,Q,H,L,P,2) float32 and grad_attn (B,Q,H,L,P).
+ */
+int msda_b200_backward(const msda_b200_desc* desc, const void* value /*dev*/, const float* loc /*dev*/,
+                       const void* attn /*dev*/, const void* grad_out /*dev*/, void* grad_value /*dev*/,
+                       float* grad_loc /*dev*/, void* grad_attn /*dev*/, void* workspace /*dev|NULL*/,
+                       size_t workspace_bytes, const int32_t* query_order /*dev|NULL*/, void* stream);
+
+/*
+ * Profiling aid for bench.py: when desc->flags has MSDA_B200_FLAG_PROFILE the library records
+ * CUDA events on `stream` around each kernel it launches.  After the stream has been
+ * synchronised, msda_b200_profile_ms(which, &ms) returns the device time of the last such launch
+ * on this thread.  `which`: one of MSDA_B200_PROF_*.
+ */
+#define MSDA_B200_PROF_FWD 0          /* forward gather kernel                                    */
+#define MSDA_B200_PROF_BWD_ZERO 1     /* zero-fill of grad_value / workspace                      */
+#define MSDA_B200_PROF_BWD_MAIN 2     /* backward gather + scatter kernel                         */
+#define MSDA_B200_PROF_BWD_CONVERT 3  /* fp32 workspace -> bf16 grad_value                        */
+#define MSDA_B200_PROF_COUNT 4
+int msda_b200_profile_ms(int which, float* ms);
+
+/* Number of kernels the library launched on this thread since the last reset (memsets not counted). */
+int64_t msda_b200_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

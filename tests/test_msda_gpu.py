@@ -1,0 +1,251 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes -> libmsda_b200.so).
+
+Bars (BASELINE.json north_star): fp32 within 1e-5 relative, bf16 within 2e-2 relative, where
+"relative" is max|a-b| / max|b| over the tensor (``conftest.rel_err``).
+Nothing here reads /root/reference; the oracle is oracle/ (C restatement) plus tests/golden/.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_BAR = 1e-5
+BF16_BAR = 2e-2
+
+
+@pytest.fixture(scope="module")
+def wis():
+    import weed_instance_segmentation_b200 as w
+    from weed_instance_segmentation_b200 import _cabi
+    _cabi.load()  # fail loudly if the extension is missing
+    assert torch.cuda.is_available()
+    return w
+
+
+def _run(wis, value, shapes, loc, attn, grad_out, level_start=None):
+    dev = "cuda"
+    v = value.to(dev).requires_grad_(True)
+    lo = loc.to(dev).requires_grad_(True)
+    a = attn.to(dev).requires_grad_(True)
+    out = wis.ms_deform_attn(v, shapes, level_start, lo, a)
+    out.backward(grad_out.to(dev).reshape(out.shape))
+    torch.cuda.synchronize()
+    return [t.detach().float().cpu().numpy() for t in (out, v.grad, lo.grad, a.grad)]
+
+
+def _oracle(value, shapes, loc, attn, grad_out, level_start=None):
+    v, lo, a, go = (t.float().numpy() for t in (value, loc, attn, grad_out))
+    out = oracle.c_forward(v, shapes, lo, a, level_start=level_start)
+    gv, gl, ga = oracle.c_backward(v, shapes, lo, a, go, level_start=level_start)
+    return out, gv, gl, ga
+
+
+def _assert_close(got, want, bar, tag):
+    for name, g, w in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
+        assert g.shape == w.shape, (tag, name)
+        e = rel_err(g, w)
+        assert e <= bar, f"{tag}: {name} rel err {e:.3e} > {bar:g}"
+
+
+# ---------------------------------------------------------------------------- golden fixtures
+def test_golden_fp32(wis, golden):
+    name, g = golden
+    shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
+    D = g["value"].shape[-1]
+    if D not in (8, 16, 32, 64, 128):
+        pytest.skip(f"head dim {D} has no kernel (documented: 8/16/32/64/128)")
+    got = _run(wis, *(torch.from_numpy(g[k]) for k in ("value",)), shapes,
+               torch.from_numpy(g["loc"]), torch.from_numpy(g["attn"]), torch.from_numpy(g["grad_out"]))
+    want = (g["out_f64"], g["grad_value_f64"], g["grad_loc_f64"], g["grad_attn_f64"])
+    _assert_close(got, want, FP32_BAR, name)
+
+
+def test_golden_bf16(wis, golden):
+    name, g = golden
+    shapes = [tuple(int(v) for v in r) for r in g["shapes"]]
+    if g["value"].shape[-1] not in (8, 16, 32, 64, 128):
+        pytest.skip("head dim without a kernel")
+    value = torch.from_numpy(g["value"]).bfloat16()
+    attn = torch.from_numpy(g["attn"]).bfloat16()
+    go = torch.from_numpy(g["grad_out"]).bfloat16()
+    loc = torch.from_numpy(g["loc"])
+    got = _run(wis, value, shapes, loc, attn, go)
+    want = _oracle(value, shapes, loc, attn, go)  # oracle on the bf16-rounded inputs, fp64 arithmetic
+    _assert_close(got, want, BF16_BAR, name)
+
+
+# ---------------------------------------------------------------------------- seeded random cases
+CASES = [
+    # (tag, B, shapes, H, D, P, Q)
+    ("c1_512", 1, [(16, 16), (32, 32), (64, 64)], 8, 32, 4, None),
+    ("c3_odd", 1, [(31, 41), (61, 81), (121, 162)], 8, 32, 4, None),
+    ("ragged_q", 3, [(5, 7), (9, 4)], 4, 32, 3, 77),
+    ("d16", 2, [(6, 6), (12, 12)], 8, 16, 4, None),
+    ("d64", 2, [(6, 6), (12, 12)], 4, 64, 2, 50),
+    ("one_pixel_levels", 2, [(1, 1), (1, 9), (7, 1), (4, 4)], 2, 32, 2, 33),
+    ("many_points", 1, [(8, 8)], 2, 32, 16, None),
+]
+
+
+@pytest.mark.parametrize("dist", ["init", "trained", "adversarial"])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_random_fp32(wis, case, dist):
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    tag, B, shapes, H, D, P, Q = case
+    x = msda_inputs(B, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=7, num_queries=Q)
+    args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    _assert_close(_run(wis, *args), _oracle(*args), FP32_BAR, f"{tag}/{dist}")
+
+
+@pytest.mark.parametrize("attn_dtype", [torch.bfloat16, torch.float32], ids=["attn_bf16", "attn_f32"])
+@pytest.mark.parametrize("dist", ["init", "trained", "adversarial"])
+@pytest.mark.parametrize("case", CASES[:4], ids=[c[0] for c in CASES[:4]])
+def test_random_bf16(wis, case, dist, attn_dtype):
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    tag, B, shapes, H, D, P, Q = case
+    x = msda_inputs(B, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=8, num_queries=Q,
+                    value_dtype=torch.bfloat16, attn_dtype=attn_dtype)
+    args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    _assert_close(_run(wis, *args), _oracle(*args), BF16_BAR, f"{tag}/{dist}")
+
+
+def test_query_order_does_not_change_results(wis, monkeypatch):
+    from weed_instance_segmentation_b200 import functional as F
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(7, 9), (13, 18)]
+    x = msda_inputs(2, shapes, dist="trained", seed=5)
+    args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    with_order = _run(wis, *args)
+    monkeypatch.setattr(F, "_USE_ORDER", False)
+    without = _run(wis, *args)
+    assert np.array_equal(with_order[0], without[0])  # forward is bit-identical
+    _assert_close(with_order, without, 1e-6, "order")  # backward differs only by atomic ordering
+
+
+def test_custom_level_start_and_padded_rows(wis):
+    """S larger than the sum of the levels, levels not packed: level_start_index is honoured."""
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(3, 4), (5, 6)]
+    x = msda_inputs(2, shapes, dist="adversarial", seed=9, num_queries=21)
+    S_pad = 60
+    value = torch.randn(2, S_pad, 8, 32)
+    lsi = [7, 25]
+    args = (value, shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    got = _run(wis, *args, level_start=lsi)
+    want = _oracle(*args, level_start=np.asarray(lsi))
+    _assert_close(got, want, FP32_BAR, "padded")
+    assert not got[1][:, :7].any() and not got[1][:, 55:].any()  # untouched rows get zero gradient
+
+
+def test_empty_and_noncontiguous(wis):
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(4, 4)]
+    v = torch.randn(2, 16, 8, 32, device="cuda")
+    out = wis.ms_deform_attn(v, shapes, None, torch.zeros(2, 0, 8, 1, 4, 2, device="cuda"),
+                             torch.zeros(2, 0, 8, 1, 4, device="cuda"))
+    assert out.shape == (2, 0, 256)
+    out = wis.ms_deform_attn(v[:0], shapes, None, torch.zeros(0, 5, 8, 1, 4, 2, device="cuda"),
+                             torch.zeros(0, 5, 8, 1, 4, device="cuda"))
+    assert out.shape == (0, 5, 256)
+    # non-contiguous views are accepted (made contiguous on the host side)
+    x = msda_inputs(2, shapes, dist="trained", seed=2)
+    vt = x["value"].permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    assert not vt.is_contiguous()
+    a = _run(wis, vt, shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    b = _run(wis, x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    assert np.array_equal(a[0], b[0])
+
+
+def test_error_behaviour(wis):
+    v = torch.zeros(1, 16, 8, 32, device="cuda")
+    loc = torch.zeros(1, 3, 8, 1, 4, 2, device="cuda")
+    attn = torch.zeros(1, 3, 8, 1, 4, device="cuda")
+    with pytest.raises(ValueError):  # shapes do not fit S (M2F:942-945)
+        wis.ms_deform_attn(v, [(5, 5)], None, loc, attn)
+    with pytest.raises(ValueError):
+        wis.ms_deform_attn(v, [(4, 4)], None, loc[..., :1], attn)
+    with pytest.raises(ValueError):
+        wis.ms_deform_attn(v, [(4, 4)], None, loc, attn[:, :2])
+    with pytest.raises(TypeError):
+        wis.ms_deform_attn(v.half(), [(4, 4)], None, loc, attn)
+    with pytest.raises(wis.MSDAError):  # head dim without a kernel: reported by the library, not swallowed
+        wis.ms_deform_attn(torch.zeros(1, 16, 8, 24, device="cuda"), [(4, 4)], None, loc, attn)
+
+
+def test_nan_and_far_locations_are_safe(wis):
+    """NaN / huge coordinates contribute zero (as in the oracle) and never fault."""
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(4, 5), (8, 9)]
+    x = msda_inputs(1, shapes, dist="adversarial", seed=4, num_queries=32)
+    loc = x["sampling_locations"].clone()
+    loc.view(-1, 2)[::7] = float("nan")
+    loc.view(-1, 2)[1::7] = 1e30
+    loc.view(-1, 2)[2::7] = -1e30
+    loc.view(-1, 2)[3::7] = float("inf")
+    args = (x["value"], shapes, loc, x["attention_weights"], x["grad_out"])
+    got, want = _run(wis, *args), _oracle(*args)
+    assert all(np.isfinite(g).all() for g in got)
+    _assert_close(got, want, FP32_BAR, "nan")
+
+
+# ---------------------------------------------------------------------------- full-size properties
+def _c2_inputs(dist, dtype):
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(32, 32), (64, 64), (128, 128)]
+    return shapes, msda_inputs(8, shapes, dist=dist, seed=1, device="cuda", value_dtype=dtype)
+
+
+@pytest.mark.parametrize("dist", ["init", "adversarial"])
+def test_full_size_linearity_and_adjoint_fp32(wis, dist):
+    """At BASELINE config 2 (B=8, 1024^2): f is linear in value and in attn, and the backward is
+    its adjoint:  <go, f(v,a)> == <grad_value, v> == <grad_attn, a>."""
+    shapes, x = _c2_inputs(dist, torch.float32)
+    v = x["value"].requires_grad_(True)
+    lo = x["sampling_locations"].requires_grad_(True)
+    a = x["attention_weights"].requires_grad_(True)
+    go = x["grad_out"]
+    out = wis.ms_deform_attn(v, shapes, x["level_start_index"], lo, a)
+    out.backward(go)
+    lhs = (go.double() * out.detach().double()).sum().item()
+    assert abs((v.grad.double() * v.detach().double()).sum().item() - lhs) <= 1e-5 * max(abs(lhs), 1.0) * 10
+    assert abs((a.grad.double() * a.detach().double()).sum().item() - lhs) <= 1e-5 * max(abs(lhs), 1.0) * 10
+    # linearity in value
+    v2 = torch.randn_like(v)
+    with torch.no_grad():
+        o2 = wis.ms_deform_attn(v2, shapes, None, lo, a)
+        o3 = wis.ms_deform_attn(v.detach() * 0.5 + v2, shapes, None, lo, a)
+    assert rel_err((0.5 * out.detach() + o2).cpu().numpy(), o3.cpu().numpy()) <= 1e-5
+    # a slice against the oracle (first 64 queries of the last batch element)
+    sl = slice(0, 64)
+    want = oracle.c_forward(v.detach()[-1:].cpu().numpy(), shapes, lo.detach()[-1:, sl].cpu().numpy(),
+                            a.detach()[-1:, sl].cpu().numpy())
+    assert rel_err(out.detach()[-1:, sl].cpu().numpy(), want) <= FP32_BAR
+
+
+def test_full_size_matches_reference_on_gpu_bf16(wis):
+    """BASELINE config 2 in the bf16 contract against the reference's own function (M2F:798-837)
+    run in fp32 on the same GPU, two batch elements at a time to bound its 2 GB temporary."""
+    pytest.importorskip("transformers")
+    from oracle.hf_reference import hf_forward_torch
+    shapes, x = _c2_inputs("trained", torch.bfloat16)
+    v = x["value"].requires_grad_(True)
+    lo = x["sampling_locations"].requires_grad_(True)
+    a = x["attention_weights"].requires_grad_(True)
+    out = wis.ms_deform_attn(v, shapes, x["level_start_index"], lo, a)
+    out.backward(x["grad_out"])
+    for b0 in range(0, 8, 2):
+        sl = slice(b0, b0 + 2)
+        rv = v.detach()[sl].float().requires_grad_(True)
+        rl = lo.detach()[sl].clone().requires_grad_(True)
+        ra = a.detach()[sl].float().requires_grad_(True)
+        ro = hf_forward_torch(rv, shapes, rl, ra)
+        ro.backward(x["grad_out"][sl].float())
+        for name, got, want in (("out", out.detach()[sl], ro.detach()), ("grad_value", v.grad[sl], rv.grad),
+                                ("grad_loc", lo.grad[sl], rl.grad), ("grad_attn", a.grad[sl], ra.grad)):
+            e = ((got.float() - want).abs().max() / want.abs().max()).item()
+            assert e <= BF16_BAR, f"batch {b0}: {name} rel err {e:.3e}"
+        del rv, rl, ra, ro

@@ -1,0 +1,26 @@
+"""B200-native multi-scale deformable attention for the Mask2Former crop/weed model.
+
+One hot path, hand-written for sm_100a behind a C ABI (``include/msda_b200.h``):
+the pixel-decoder MSDeformAttn that ``marco-conciatori-public/weed_instance_segmentation``
+runs through HuggingFace ``transformers`` (M2F:798-837). See DESIGN.md and INTEGRATION.md.
+"""
+from .functional import (  # noqa: F401
+    MSDAError,
+    MSDeformAttnFunction,
+    ms_deform_attn,
+    multi_scale_deformable_attention,
+    query_order_2d,
+)
+from .hf_patch import install, installed, is_installed, uninstall  # noqa: F401
+
+__all__ = [
+    "MSDAError",
+    "MSDeformAttnFunction",
+    "ms_deform_attn",
+    "multi_scale_deformable_attention",
+    "query_order_2d",
+    "install",
+    "installed",
+    "is_installed",
+    "uninstall",
+]

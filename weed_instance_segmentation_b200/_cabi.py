@@ -1,0 +1,110 @@
+"""ctypes binding of ``include/msda_b200.h`` (the drop-in C ABI).
+
+The library is mandatory: using any compute entry point without
+``libmsda_b200.so`` raises. There is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
+
+ABI_VERSION = 1
+MAX_LEVELS = 8
+F32, BF16 = 0, 1
+FLAG_PROFILE = 1
+FLAG_BF16_ATOMICS = 2
+PROF_FWD, PROF_BWD_ZERO, PROF_BWD_MAIN, PROF_BWD_CONVERT = 0, 1, 2, 3
+
+# every symbol include/msda_b200.h declares
+EXPORTS = (
+    "msda_b200_abi_version",
+    "msda_b200_last_error",
+    "msda_b200_forward",
+    "msda_b200_backward_workspace_bytes",
+    "msda_b200_backward",
+    "msda_b200_profile_ms",
+    "msda_b200_launch_count",
+)
+
+
+class Desc(ctypes.Structure):
+    """``msda_b200_desc``."""
+
+    _fields_ = [
+        ("B", ctypes.c_int32), ("S", ctypes.c_int32), ("Q", ctypes.c_int32), ("H", ctypes.c_int32),
+        ("D", ctypes.c_int32), ("L", ctypes.c_int32), ("P", ctypes.c_int32),
+        ("value_dtype", ctypes.c_int32), ("attn_dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
+        ("spatial_shapes_hw", ctypes.POINTER(ctypes.c_int32)),
+        ("level_start_index", ctypes.POINTER(ctypes.c_int64)),
+    ]
+
+
+class MSDAError(RuntimeError):
+    """A non-zero return code from the C ABI."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"msda_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load ``libmsda_b200.so`` (building nothing; see ``build.py``). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing. Build it with `python -m weed_instance_segmentation_b200.build` "
+            "(needs nvcc). This package has no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    dp = ctypes.POINTER(Desc)
+    lib.msda_b200_abi_version.restype = ctypes.c_int
+    lib.msda_b200_abi_version.argtypes = []
+    lib.msda_b200_last_error.restype = ctypes.c_char_p
+    lib.msda_b200_last_error.argtypes = []
+    lib.msda_b200_forward.restype = ctypes.c_int
+    lib.msda_b200_forward.argtypes = [dp, vp, vp, vp, vp, vp, vp]
+    lib.msda_b200_backward_workspace_bytes.restype = ctypes.c_size_t
+    lib.msda_b200_backward_workspace_bytes.argtypes = [dp]
+    lib.msda_b200_backward.restype = ctypes.c_int
+    lib.msda_b200_backward.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]
+    lib.msda_b200_profile_ms.restype = ctypes.c_int
+    lib.msda_b200_profile_ms.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.msda_b200_launch_count.restype = ctypes.c_int64
+    lib.msda_b200_launch_count.argtypes = [ctypes.c_int]
+    got = lib.msda_b200_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {got}, expected {ABI_VERSION}; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MSDAError(rc, load().msda_b200_last_error().decode())
+
+
+def make_desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, shapes_hw, level_start, flags=0):
+    """Build a ``Desc`` plus the host arrays it points to (keep the returned tuple alive)."""
+    shp = (ctypes.c_int32 * (2 * L))(*[int(v) for hw in shapes_hw for v in hw])
+    lsi = (ctypes.c_int64 * L)(*[int(v) for v in level_start])
+    d = Desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, flags, shp, lsi)
+    return d, (shp, lsi)
+
+
+def profile_ms(which: int) -> float:
+    ms = ctypes.c_float(0.0)
+    check(load().msda_b200_profile_ms(which, ctypes.byref(ms)))
+    return float(ms.value)
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().msda_b200_launch_count(1 if reset else 0))

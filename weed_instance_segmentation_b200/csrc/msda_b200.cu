@@ -1,0 +1,649 @@
+// msda_b200.cu -- multi-scale deformable attention, forward + backward, for sm_100a (B200).
+//
+// Replaces transformers/models/mask2former/modeling_mask2former.py:798-837 (M2F:798) and the
+// autograd graph behind it; C ABI in include/msda_b200.h.  See DESIGN.md for the data layout,
+// the roofline of each kernel and the scheduling rationale.
+//
+// Kernel plan (one thread block = one (batch, head, tile of TQ queries)):
+//   phase 1  every thread turns (loc, attn) of one sample into a *descriptor* in shared memory:
+//            four slot weights, the 16-byte-unit offset of the top-left slot, done once per sample
+//            instead of once per lane that touches the sample;
+//   phase 2  LPP = D*sizeof(T)/16 lanes own one (query, head) pair and stream the L*P samples:
+//            one broadcast LDS.128 for the weights, four 128-bit value loads (the 2x2 bilinear
+//            footprint; each corner is one contiguous D*sizeof(T)-byte run), fp32 FMAs;
+//   phase 3  (backward only) one thread per sample folds the per-lane partial dot products into
+//            grad_attn / grad_loc.
+//
+// Out-of-range corners: the 2x2 footprint is clamped into the level and the bilinear weights are
+// re-slotted (a corner that falls outside gets weight 0, the surviving one moves to the slot that
+// is actually loaded), so phase 2 has no bounds checks and never forms an out-of-bounds address.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_b200.h"
+
+namespace {
+
+constexpr int kMaxL = MSDA_B200_MAX_LEVELS;
+
+struct Level {
+  int H, W;
+  int start;  // first row of this level in S
+  int dx16;   // +1 pixel in x, in 16-byte units of the value tensor (0 if W == 1)
+  int dy16;   // +1 pixel in y, in 16-byte units (0 if H == 1)
+};
+
+struct KParams {
+  const void* value;
+  const float* loc;
+  const void* attn;
+  void* out;             // forward
+  const void* grad_out;  // backward
+  void* grad_value_acc;  // backward: fp32 accumulator (grad_value itself for fp32) or bf16 grad_value
+  float* grad_loc;
+  void* grad_attn;
+  const int* q_order;
+  int B, S, Q, H, L, P, LP;
+  int num_tiles;
+  long long batch_stride16;  // S*H*D*sizeof(T)/16
+  Level lv[kMaxL];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Sample descriptor maths (shared by forward and backward).
+// ---------------------------------------------------------------------------------------------
+struct Axis {
+  float s0, s1;  // weights of the two loaded slots (base, base+1)
+  float g0, g1;  // d(s0)/d(pixel coord), d(s1)/d(pixel coord)
+  int base;      // clamped index of slot 0
+  bool ok;
+};
+
+// coord: normalised location in [0,1] (may lie outside); n: level extent along this axis.
+// Follows M2F:807 (grid = 2*loc - 1) and ATen grid_sampler_unnormalize(align_corners=False):
+//   pix = ((grid + 1) * n - 1) / 2, evaluated in that order without FMA contraction.
+__device__ __forceinline__ Axis axis_setup(float coord, int n) {
+  Axis a;
+  const float g = __fadd_rn(__fmul_rn(2.f, coord), -1.f);
+  const float pix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)n), -1.f), 0.5f);
+  a.ok = (pix > -2.f) && (pix < (float)(n + 1));  // false for NaN as well
+  const float fl = floorf(pix);
+  const int i0 = __float2int_rd(pix);  // saturating; NaN -> 0
+  const float l = pix - fl;
+  const bool v0 = (i0 >= 0) && (i0 < n);
+  const bool v1 = (i0 + 1 >= 0) && (i0 + 1 < n);
+  const float w0 = v0 ? 1.f - l : 0.f, w1 = v1 ? l : 0.f;
+  const float d0 = v0 ? -1.f : 0.f, d1 = v1 ? 1.f : 0.f;
+  const int ib = min(max(i0, 0), max(n - 2, 0));
+  const int shift = i0 - ib;
+  a.base = ib;
+  a.s0 = (shift == 0) ? w0 : ((shift == -1) ? w1 : 0.f);
+  a.g0 = (shift == 0) ? d0 : ((shift == -1) ? d1 : 0.f);
+  a.s1 = (shift == 0) ? w1 : ((shift == 1) ? w0 : 0.f);
+  a.g1 = (shift == 0) ? d1 : ((shift == 1) ? d0 : 0.f);
+  return a;
+}
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16 bytes of T -> VEC floats
+template <typename T>
+struct Vec16;
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+template <>
+struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
+    // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked.
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+  static __device__ __forceinline__ unsigned pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&h);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+};
+
+__device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
+
+// red.global.add.v4.f32 (sm_90+): one 16-byte reduction, no return value.
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+// red.global.add.noftz.v4.bf16x2 (sm_90+): eight bf16 lanes in one 16-byte reduction.
+__device__ __forceinline__ void red_add_bf16x8(void* addr, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+
+template <int NT, int LPP, int QPG>
+struct Tile {
+  static constexpr int NG = NT / LPP;   // (query, head) pairs in flight per block
+  static constexpr int TQ = NG * QPG;   // queries per block
+  static constexpr int ROW = TQ + 1;    // padded row of the [sample][query] descriptor arrays
+};
+
+__device__ __forceinline__ void decode_block(const KParams& p, int& b, int& tile, int& h) {
+  int bid = blockIdx.x;
+  h = bid % p.H;
+  bid /= p.H;
+  tile = bid % p.num_tiles;
+  b = bid / p.num_tiles;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward
+// ---------------------------------------------------------------------------------------------
+template <typename VT, typename AT, int D, int NT, int QPG>
+__global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KParams p) {
+  constexpr int VEC = Vec16<VT>::N;
+  constexpr int LPP = D / VEC;
+  using T = Tile<NT, LPP, QPG>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sw = reinterpret_cast<float4*>(smem_raw);                    // [LP][ROW] slot weights * attn
+  int* soff = reinterpret_cast<int*>(smem_raw + (size_t)p.LP * T::ROW * sizeof(float4));  // [LP][ROW]
+
+  int b, tile, h;
+  decode_block(p, b, tile, h);
+  const int q0 = tile * T::TQ;
+  const int nq = min(T::TQ, p.Q - q0);
+  const int LP = p.LP;
+
+  // ---- phase 1: descriptors
+  for (int i = threadIdx.x; i < nq * LP; i += NT) {
+    const int ql = i / LP, s = i - ql * LP;
+    const int l = s / p.P;
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
+    const Level lv = p.lv[l];
+    const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
+    const bool ok = ax.ok && ay.ok;
+    const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
+    sw[s * T::ROW + ql] = make_float4(wt * ax.s0, wt * ax.s1, wb * ax.s0, wb * ax.s1);
+    soff[s * T::ROW + ql] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+  }
+  __syncthreads();
+
+  // ---- phase 2: gather
+  const int g = threadIdx.x / LPP, c = threadIdx.x % LPP;
+  const uint4* vb = reinterpret_cast<const uint4*>(p.value) + (long long)b * p.batch_stride16 + c;
+#pragma unroll
+  for (int it = 0; it < QPG; ++it) {
+    const int ql = g + it * T::NG;
+    if (ql >= nq) break;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      const int dx = p.lv[l].dx16, dy = p.lv[l].dy16;
+#pragma unroll 4
+      for (int pt = 0; pt < p.P; ++pt) {
+        const int s = l * p.P + pt;
+        const float4 w = sw[s * T::ROW + ql];
+        const uint4* ptr = vb + soff[s * T::ROW + ql];
+        const uint4 v00 = ldg16(ptr), v01 = ldg16(ptr + dx), v10 = ldg16(ptr + dy), v11 = ldg16(ptr + dy + dx);
+        float f[VEC];
+        Vec16<VT>::unpack(v00, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.x, f[j], acc[j]);
+        Vec16<VT>::unpack(v01, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.y, f[j], acc[j]);
+        Vec16<VT>::unpack(v10, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.z, f[j], acc[j]);
+        Vec16<VT>::unpack(v11, f);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.w, f[j], acc[j]);
+      }
+    }
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    uint4* o = reinterpret_cast<uint4*>(p.out) + (((long long)b * p.Q + q) * p.H + h) * LPP + c;
+    *o = Vec16<VT>::pack(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward
+// ---------------------------------------------------------------------------------------------
+// ACC: 0 = fp32 accumulator with red.v4.f32 (grad_value itself for fp32 values, workspace for bf16)
+//      1 = bf16 grad_value accumulated in place with red.v4.bf16x2 (MSDA_B200_FLAG_BF16_ATOMICS)
+template <typename VT, typename AT, int D, int NT, int QPG, int ACC>
+__global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KParams p) {
+  constexpr int VEC = Vec16<VT>::N;
+  constexpr int LPP = D / VEC;
+  using T = Tile<NT, LPP, QPG>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int LP = p.LP;
+  const size_t n = (size_t)LP * T::ROW;
+  float4* ss = reinterpret_cast<float4*>(smem_raw);     // [LP][ROW] (sL, sR, sT, sB)
+  float4* sg = ss + n;                                  // [LP][ROW] (gL, gR, gT, gB)
+  float4* sd = sg + n;                                  // [LP][TQ][LPP] per-lane partial dots
+  float* sa = reinterpret_cast<float*>(sd + (size_t)LP * T::TQ * LPP);  // [LP][ROW] attn
+  int* soff = reinterpret_cast<int*>(sa + n);           // [LP][ROW]
+
+  int b, tile, h;
+  decode_block(p, b, tile, h);
+  const int q0 = tile * T::TQ;
+  const int nq = min(T::TQ, p.Q - q0);
+
+  // ---- phase 1: descriptors
+  for (int i = threadIdx.x; i < nq * LP; i += NT) {
+    const int ql = i / LP, s = i - ql * LP;
+    const int l = s / p.P;
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
+    const Level lv = p.lv[l];
+    const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
+    const bool ok = ax.ok && ay.ok;
+    const int k = s * T::ROW + ql;
+    ss[k] = ok ? make_float4(ax.s0, ax.s1, ay.s0, ay.s1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sg[k] = ok ? make_float4(ax.g0, ax.g1, ay.g0, ay.g1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sa[k] = a;
+    soff[k] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+  }
+  __syncthreads();
+
+  // ---- phase 2: gather value corners, scatter grad_value, per-lane partial dots
+  const int g = threadIdx.x / LPP, c = threadIdx.x % LPP;
+  const uint4* vb = reinterpret_cast<const uint4*>(p.value) + (long long)b * p.batch_stride16 + c;
+#pragma unroll
+  for (int it = 0; it < QPG; ++it) {
+    const int ql = g + it * T::NG;
+    if (ql >= nq) break;
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    float go[VEC];
+    {
+      const uint4 gv = ldg16(reinterpret_cast<const uint4*>(p.grad_out) + (((long long)b * p.Q + q) * p.H + h) * LPP + c);
+      Vec16<VT>::unpack(gv, go);
+    }
+    for (int l = 0; l < p.L; ++l) {
+      const int dx = p.lv[l].dx16, dy = p.lv[l].dy16;
+#pragma unroll 2
+      for (int pt = 0; pt < p.P; ++pt) {
+        const int s = l * p.P + pt;
+        const int k = s * T::ROW + ql;
+        const float4 w = ss[k];
+        const float a = sa[k];
+        const int off = soff[k];
+        const uint4* ptr = vb + off;
+        const uint4 v[4] = {ldg16(ptr), ldg16(ptr + dx), ldg16(ptr + dy), ldg16(ptr + dy + dx)};
+        const float wc[4] = {a * w.z * w.x, a * w.z * w.y, a * w.w * w.x, a * w.w * w.y};
+        const int coff[4] = {0, dx, dy, dy + dx};
+        float dot[4];
+#pragma unroll
+        for (int cn = 0; cn < 4; ++cn) {
+          float f[VEC];
+          Vec16<VT>::unpack(v[cn], f);
+          float d = 0.f;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) d = fmaf(go[j], f[j], d);
+          dot[cn] = d;
+          if (wc[cn] != 0.f) {
+            // element offset of this lane's 16 bytes inside grad_value
+            const long long e = ((long long)b * p.batch_stride16 + off + coff[cn] + c) * VEC;
+            if (ACC == 0) {
+              float* dst = reinterpret_cast<float*>(p.grad_value_acc) + e;
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4)
+                red_add_f32x4(dst + j, wc[cn] * go[j], wc[cn] * go[j + 1], wc[cn] * go[j + 2], wc[cn] * go[j + 3]);
+            } else {
+              float t[VEC];
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) t[j] = wc[cn] * go[j];
+              const uint4 pk = Vec16<VT>::pack(t);
+              red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + e, pk.x, pk.y, pk.z, pk.w);
+            }
+          }
+        }
+        sd[((size_t)s * T::TQ + ql) * LPP + c] = make_float4(dot[0], dot[1], dot[2], dot[3]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 3: per-sample gradients of attention weights and sampling locations
+  for (int i = threadIdx.x; i < nq * LP; i += NT) {
+    const int ql = i / LP, s = i - ql * LP;
+    const int l = s / p.P;
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* part = sd + ((size_t)s * T::TQ + ql) * LPP;
+#pragma unroll
+    for (int j = 0; j < LPP; ++j) {
+      const float4 t = part[j];
+      d.x += t.x; d.y += t.y; d.z += t.z; d.w += t.w;
+    }
+    const int k = s * T::ROW + ql;
+    const float4 w = ss[k], gw = sg[k];
+    const float a = sa[k];
+    // d.x=(top,left) d.y=(top,right) d.z=(bottom,left) d.w=(bottom,right)
+    const float top_s = w.x * d.x + w.y * d.y, bot_s = w.x * d.z + w.y * d.w;
+    const float top_g = gw.x * d.x + gw.y * d.y, bot_g = gw.x * d.z + gw.y * d.w;
+    const float g_attn = w.z * top_s + w.w * bot_s;
+    const float g_px = w.z * top_g + w.w * bot_g;
+    const float g_py = gw.z * top_s + gw.w * bot_s;
+    reinterpret_cast<AT*>(p.grad_attn)[si] = from_float<AT>(g_attn);
+    reinterpret_cast<float2*>(p.grad_loc)[si] = make_float2((float)p.lv[l].W * a * g_px, (float)p.lv[l].H * a * g_py);
+  }
+}
+
+// fp32 accumulator -> bf16 grad_value, 8 elements per thread
+__global__ void __launch_bounds__(256) msda_cvt_f32_bf16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst,
+                                                               long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(src + 2 * i), b2 = __ldcs(src + 2 * i + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b2.x, b2.y, b2.z, b2.w};
+    __stcs(dst + i, Vec16<__nv_bfloat16>::pack(f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct Prof {
+  int device = -1;
+  cudaEvent_t ev[MSDA_B200_PROF_COUNT][2];
+  bool valid[MSDA_B200_PROF_COUNT] = {};
+};
+thread_local Prof g_prof;
+
+bool prof_prepare() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_prof.device == dev) return true;
+  if (g_prof.device >= 0) {
+    // events belong to another device's context; leak them rather than switch devices here
+  }
+  for (int i = 0; i < MSDA_B200_PROF_COUNT; ++i) {
+    if (cudaEventCreate(&g_prof.ev[i][0]) != cudaSuccess) return false;
+    if (cudaEventCreate(&g_prof.ev[i][1]) != cudaSuccess) return false;
+    g_prof.valid[i] = false;
+  }
+  g_prof.device = dev;
+  return true;
+}
+
+struct ProfScope {
+  int which;
+  cudaStream_t st;
+  bool on;
+  ProfScope(bool enabled, int w, cudaStream_t s) : which(w), st(s), on(enabled && prof_prepare()) {
+    if (on) cudaEventRecord(g_prof.ev[which][0], st);
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(g_prof.ev[which][1], st);
+      g_prof.valid[which] = true;
+    }
+  }
+};
+
+size_t dtype_size(int dt) { return dt == MSDA_B200_BF16 ? 2 : 4; }
+
+int validate(const msda_b200_desc* d) {
+  if (!d) return fail(MSDA_B200_ERR_INVALID, "desc is NULL");
+  if (d->B < 0 || d->S < 0 || d->Q < 0) return fail(MSDA_B200_ERR_INVALID, "negative B/S/Q (%d, %d, %d)", d->B, d->S, d->Q);
+  if (d->H <= 0 || d->D <= 0 || d->L <= 0 || d->P <= 0)
+    return fail(MSDA_B200_ERR_INVALID, "H, D, L, P must be positive (%d, %d, %d, %d)", d->H, d->D, d->L, d->P);
+  if (d->L > kMaxL) return fail(MSDA_B200_ERR_UNSUPPORTED, "L=%d exceeds MSDA_B200_MAX_LEVELS=%d", d->L, kMaxL);
+  if (d->value_dtype != MSDA_B200_F32 && d->value_dtype != MSDA_B200_BF16)
+    return fail(MSDA_B200_ERR_UNSUPPORTED, "value_dtype %d (want 0=f32 or 1=bf16)", d->value_dtype);
+  if (d->attn_dtype != MSDA_B200_F32 && d->attn_dtype != MSDA_B200_BF16)
+    return fail(MSDA_B200_ERR_UNSUPPORTED, "attn_dtype %d (want 0=f32 or 1=bf16)", d->attn_dtype);
+  if (d->value_dtype == MSDA_B200_F32 && d->attn_dtype != MSDA_B200_F32)
+    return fail(MSDA_B200_ERR_UNSUPPORTED, "fp32 values need fp32 attention weights");
+  if (d->D != 8 && d->D != 16 && d->D != 32 && d->D != 64 && d->D != 128)
+    return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim D=%d (kernels exist for 8, 16, 32, 64, 128)", d->D);
+  if (!d->spatial_shapes_hw || !d->level_start_index)
+    return fail(MSDA_B200_ERR_INVALID, "spatial_shapes_hw / level_start_index is NULL");
+  for (int l = 0; l < d->L; ++l) {
+    const long long hh = d->spatial_shapes_hw[2 * l], ww = d->spatial_shapes_hw[2 * l + 1];
+    const long long st = d->level_start_index[l];
+    if (hh <= 0 || ww <= 0) return fail(MSDA_B200_ERR_INVALID, "level %d has non-positive shape (%lld, %lld)", l, hh, ww);
+    if (st < 0 || st + hh * ww > d->S)
+      return fail(MSDA_B200_ERR_INVALID, "level %d rows [%lld, %lld) fall outside S=%d", l, st, st + hh * ww, d->S);
+  }
+  const long long per_batch = (long long)d->S * d->H * d->D * (long long)dtype_size(d->value_dtype) / 16;
+  if (per_batch >= (1ll << 31)) return fail(MSDA_B200_ERR_UNSUPPORTED, "S*H*D too large for 32-bit tile offsets");
+  if ((long long)d->L * d->P > 64) return fail(MSDA_B200_ERR_UNSUPPORTED, "L*P=%d exceeds 64", d->L * d->P);
+  return MSDA_B200_OK;
+}
+
+// Geometry fields of KParams; the tensor pointers are set by the caller beforehand.
+void fill_geometry(const msda_b200_desc* d, KParams& p, int tq) {
+  p.B = d->B; p.S = d->S; p.Q = d->Q; p.H = d->H; p.L = d->L; p.P = d->P; p.LP = d->L * d->P;
+  p.num_tiles = (d->Q + tq - 1) / tq;
+  const int per_pixel16 = d->H * d->D * (int)dtype_size(d->value_dtype) / 16;
+  p.batch_stride16 = (long long)d->S * per_pixel16;
+  for (int l = 0; l < d->L; ++l) {
+    Level& lv = p.lv[l];
+    lv.H = d->spatial_shapes_hw[2 * l];
+    lv.W = d->spatial_shapes_hw[2 * l + 1];
+    lv.start = (int)d->level_start_index[l];
+    lv.dx16 = lv.W > 1 ? per_pixel16 : 0;
+    lv.dy16 = lv.H > 1 ? lv.W * per_pixel16 : 0;
+  }
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MSDA_B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return MSDA_B200_OK;
+}
+
+// Launch geometry: NT threads per block, QPG queries per lane group.
+constexpr int kFwdNT = 256, kFwdQPG = 1;
+constexpr int kBwdNT = 128, kBwdQPG = 1;
+
+template <typename VT, typename AT, int D>
+int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
+  constexpr int LPP = D / Vec16<VT>::N;
+  using T = Tile<kFwdNT, LPP, kFwdQPG>;
+  fill_geometry(d, p, T::TQ);
+  const size_t smem = (size_t)p.LP * T::ROW * (sizeof(float4) + sizeof(int));
+  auto kern = msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
+  const long long blocks = (long long)p.B * p.num_tiles * p.H;
+  if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "forward: grid too large");
+  {
+    ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_FWD, st);
+    kern<<<(unsigned)blocks, kFwdNT, smem, st>>>(p);
+    ++g_launches;
+  }
+  return check_launch("msda_b200_forward");
+}
+
+template <typename VT, typename AT, int D, int ACC>
+int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
+  constexpr int LPP = D / Vec16<VT>::N;
+  using T = Tile<kBwdNT, LPP, kBwdQPG>;
+  fill_geometry(d, p, T::TQ);
+  const size_t n = (size_t)p.LP * T::ROW;
+  const size_t smem =
+      n * (2 * sizeof(float4) + sizeof(float) + sizeof(int)) + (size_t)p.LP * T::TQ * LPP * sizeof(float4);
+  auto kern = msda_bwd_kernel<VT, AT, D, kBwdNT, kBwdQPG, ACC>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
+  const long long blocks = (long long)p.B * p.num_tiles * p.H;
+  if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "backward: grid too large");
+  {
+    ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_BWD_MAIN, st);
+    kern<<<(unsigned)blocks, kBwdNT, smem, st>>>(p);
+    ++g_launches;
+  }
+  return check_launch("msda_b200_backward");
+}
+
+template <typename VT, typename AT>
+int dispatch_fwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
+  switch (d->D) {
+    case 8: return launch_fwd<VT, AT, 8>(d, p, st);
+    case 128: return launch_fwd<VT, AT, 128>(d, p, st);
+    case 16: return launch_fwd<VT, AT, 16>(d, p, st);
+    case 32: return launch_fwd<VT, AT, 32>(d, p, st);
+    case 64: return launch_fwd<VT, AT, 64>(d, p, st);
+  }
+  return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim %d", d->D);
+}
+
+template <typename VT, typename AT, int ACC>
+int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
+  switch (d->D) {
+    case 8: return launch_bwd<VT, AT, 8, ACC>(d, p, st);
+    case 128: return launch_bwd<VT, AT, 128, ACC>(d, p, st);
+    case 16: return launch_bwd<VT, AT, 16, ACC>(d, p, st);
+    case 32: return launch_bwd<VT, AT, 32, ACC>(d, p, st);
+    case 64: return launch_bwd<VT, AT, 64, ACC>(d, p, st);
+  }
+  return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim %d", d->D);
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char* msda_b200_last_error(void) { return g_err; }
+
+int msda_b200_forward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn, void* out,
+                      const int32_t* query_order, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  if ((long long)desc->B * desc->Q == 0) return MSDA_B200_OK;
+  if (!value || !loc || !attn || !out) return fail(MSDA_B200_ERR_INVALID, "forward: NULL tensor pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.loc = loc; p.attn = attn; p.out = out; p.q_order = query_order;
+  const bool vbf = desc->value_dtype == MSDA_B200_BF16, abf = desc->attn_dtype == MSDA_B200_BF16;
+  if (!vbf) return dispatch_fwd<float, float>(desc, p, st);
+  if (abf) return dispatch_fwd<__nv_bfloat16, __nv_bfloat16>(desc, p, st);
+  return dispatch_fwd<__nv_bfloat16, float>(desc, p, st);
+}
+
+size_t msda_b200_backward_workspace_bytes(const msda_b200_desc* desc) {
+  if (!desc) return 0;
+  if (desc->value_dtype == MSDA_B200_BF16 && !(desc->flags & MSDA_B200_FLAG_BF16_ATOMICS))
+    return (size_t)desc->B * desc->S * desc->H * desc->D * sizeof(float);
+  return 0;
+}
+
+int msda_b200_backward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn,
+                       const void* grad_out, void* grad_value, float* grad_loc, void* grad_attn, void* workspace,
+                       size_t workspace_bytes, const int32_t* query_order, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool prof = (desc->flags & MSDA_B200_FLAG_PROFILE) != 0;
+  const bool vbf = desc->value_dtype == MSDA_B200_BF16, abf = desc->attn_dtype == MSDA_B200_BF16;
+  const bool bf16_atomics = vbf && (desc->flags & MSDA_B200_FLAG_BF16_ATOMICS);
+  const size_t nvalue = (size_t)desc->B * desc->S * desc->H * desc->D;
+  const size_t need = msda_b200_backward_workspace_bytes(desc);
+  if (nvalue && !grad_value) return fail(MSDA_B200_ERR_INVALID, "backward: grad_value is NULL");
+  if (need && nvalue && (!workspace || workspace_bytes < need))
+    return fail(MSDA_B200_ERR_WORKSPACE, "backward: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  if (nvalue && need && (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return fail(MSDA_B200_ERR_INVALID, "backward: workspace must be 16-byte aligned");
+
+  // Zero-fill the accumulator (and grad_value): the scatter only touches sampled pixels.
+  void* acc = need ? workspace : grad_value;
+  if (nvalue) {
+    ProfScope ps(prof, MSDA_B200_PROF_BWD_ZERO, st);
+    const size_t acc_bytes = need ? need : nvalue * dtype_size(desc->value_dtype);
+    if (cudaMemsetAsync(acc, 0, acc_bytes, st) != cudaSuccess) return check_launch("backward: memset");
+  }
+  if ((long long)desc->B * desc->Q != 0) {
+    if (!value || !loc || !attn || !grad_out || !grad_loc || !grad_attn)
+      return fail(MSDA_B200_ERR_INVALID, "backward: NULL tensor pointer");
+    KParams p;
+    memset(&p, 0, sizeof(p));
+    p.value = value; p.loc = loc; p.attn = attn; p.grad_out = grad_out; p.grad_value_acc = acc;
+    p.grad_loc = grad_loc; p.grad_attn = grad_attn; p.q_order = query_order;
+    int rc;
+    if (!vbf) rc = dispatch_bwd<float, float, 0>(desc, p, st);
+    else if (bf16_atomics) rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 1>(desc, p, st)
+                                    : dispatch_bwd<__nv_bfloat16, float, 1>(desc, p, st);
+    else rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 0>(desc, p, st)
+                  : dispatch_bwd<__nv_bfloat16, float, 0>(desc, p, st);
+    if (rc) return rc;
+  }
+  if (need && nvalue) {
+    ProfScope ps(prof, MSDA_B200_PROF_BWD_CONVERT, st);
+    const long long n8 = (long long)(nvalue / 8);  // D is a multiple of 8, so nvalue % 8 == 0
+    const int blocks = (int)((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+    msda_cvt_f32_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(workspace),
+                                                     reinterpret_cast<uint4*>(grad_value), n8);
+    ++g_launches;
+    if (int rc = check_launch("backward: convert")) return rc;
+  }
+  return MSDA_B200_OK;
+}
+
+int msda_b200_profile_ms(int which, float* ms) {
+  if (which < 0 || which >= MSDA_B200_PROF_COUNT || !ms) return fail(MSDA_B200_ERR_INVALID, "profile_ms: bad argument");
+  if (g_prof.device < 0 || !g_prof.valid[which]) return fail(MSDA_B200_ERR_INVALID, "profile_ms: nothing recorded");
+  const cudaError_t e = cudaEventElapsedTime(ms, g_prof.ev[which][0], g_prof.ev[which][1]);
+  if (e != cudaSuccess) return fail(MSDA_B200_ERR_CUDA, "profile_ms: %s", cudaGetErrorString(e));
+  return MSDA_B200_OK;
+}
+
+int64_t msda_b200_launch_count(int reset) {
+  const long long n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+}  // extern "C"
