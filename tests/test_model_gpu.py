@@ -1,0 +1,113 @@
+"""The B200 operator dropped into the reference's model (HF Mask2Former) vs the unmodified model.
+
+Same weights, same synthetic inputs; compares logits, loss, parameter gradients and the
+post-processed per-instance masks (north_star: "per-instance mask IoU unchanged on the synthetic
+eval set"). The reference path here is the stock HF module graph (M2F:798-837 grid_sample op).
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(decoder_layers=4, encoder_layers=6, num_queries=20, train_num_points=256)
+
+
+@pytest.fixture(scope="module")
+def models():
+    pytest.importorskip("transformers")
+    from weed_instance_segmentation_b200 import _cabi, train
+    _cabi.load()
+    ref = train.build_model("swin_tiny_test", num_labels=3, seed=0, **CFG).cuda()
+    fn = copy.deepcopy(ref)
+    mod = copy.deepcopy(ref)
+    return ref, fn, mod
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+
+
+def _forward(model, batch, patched):
+    import weed_instance_segmentation_b200 as wis
+    torch.manual_seed(1234)  # the loss samples random points (M2F:619-631)
+    if patched:
+        with wis.installed():
+            return model(pixel_values=batch["pixel_values"], mask_labels=batch["mask_labels"],
+                         class_labels=batch["class_labels"])
+    assert not wis.is_installed()
+    return model(pixel_values=batch["pixel_values"], mask_labels=batch["mask_labels"], class_labels=batch["class_labels"])
+
+
+@pytest.mark.parametrize("size", [(128, 160), (97, 130)])
+def test_logits_loss_and_grads_match_reference(models, size):
+    from weed_instance_segmentation_b200 import _cabi, modules, synth
+    ref, fn, mod = models
+    modules.convert_pixel_decoder(mod)
+    batch = synth.collate_batch(2, size[0], size[1], num_classes=3, max_instances=4, seed=3, device="cuda")
+    outs = {}
+    for name, model, patched in (("ref", ref, False), ("fn", fn, True), ("mod", mod, True)):
+        model.train()
+        model.zero_grad(set_to_none=True)
+        _cabi.launch_count(reset=True)
+        out = _forward(model, batch, patched)
+        out.loss.backward()
+        outs[name] = (out, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+                      _cabi.launch_count())
+    assert outs["ref"][2] == 0 and outs["fn"][2] >= 6 * 2 and outs["mod"][2] >= 6 * 2  # 6 layers fwd + bwd kernels
+    for name in ("fn", "mod"):
+        o, g, _ = outs[name]
+        r, rg, _ = outs["ref"]
+        assert _rel(o.masks_queries_logits, r.masks_queries_logits) < 1e-4, name
+        assert _rel(o.class_queries_logits, r.class_queries_logits) < 1e-4, name
+        assert abs(o.loss.item() - r.loss.item()) < 1e-4 * abs(r.loss.item()), name
+        assert set(g) == set(rg)
+        worst = max((_rel(g[k], rg[k]), k) for k in rg if rg[k].abs().max() > 1e-6)
+        assert worst[0] < 2e-3, (name, worst)
+
+
+def test_instance_masks_unchanged(models):
+    """post_process_instance_segmentation (the reference's eval path, models/metrics.py:58-63) yields the
+    same instances: per-instance mask IoU == 1 between the stock and the B200 model."""
+    from transformers import Mask2FormerImageProcessor
+    import weed_instance_segmentation_b200 as wis
+    from weed_instance_segmentation_b200 import synth
+    ref, fn, _ = models
+    proc = Mask2FormerImageProcessor()
+    ious = []
+    for seed in range(3):
+        batch = synth.collate_batch(2, 128, 160, num_classes=3, max_instances=4, seed=20 + seed, device="cuda")
+        with torch.no_grad():
+            ref.eval(), fn.eval()
+            o_ref = ref(pixel_values=batch["pixel_values"])
+            with wis.installed():
+                o_b200 = fn(pixel_values=batch["pixel_values"])
+        kw = dict(threshold=0.0, mask_threshold=0.5, target_sizes=batch["target_sizes"])
+        p_ref = proc.post_process_instance_segmentation(o_ref, **kw)
+        p_new = proc.post_process_instance_segmentation(o_b200, **kw)
+        for a, b in zip(p_ref, p_new):
+            sa, sb = a["segmentation"], b["segmentation"]
+            ids = [int(i) for i in sa.unique().tolist() if i >= 0]
+            assert len(a["segments_info"]) == len(b["segments_info"])
+            for i in ids:
+                ma, mb = sa == i, sb == i
+                ious.append((ma & mb).sum().item() / max((ma | mb).sum().item(), 1))
+    assert ious, "no instances produced; lower the threshold"
+    assert min(ious) >= 0.999, min(ious)
+
+
+def test_bf16_autocast_forward_close(models):
+    from weed_instance_segmentation_b200 import synth
+    import weed_instance_segmentation_b200 as wis
+    ref, fn, _ = models
+    batch = synth.collate_batch(2, 128, 160, num_classes=3, max_instances=4, seed=5, device="cuda")
+    ref.eval(), fn.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        o_ref = ref(pixel_values=batch["pixel_values"])
+        with wis.installed():
+            o_new = fn(pixel_values=batch["pixel_values"])
+    # both runs carry bf16 rounding everywhere; the op itself stays within the 2e-2 bar (test_msda_gpu),
+    # the model output within a loose multiple of it
+    assert _rel(o_new.masks_queries_logits, o_ref.masks_queries_logits) < 1e-1
+    assert _rel(o_new.class_queries_logits, o_ref.class_queries_logits) < 1e-1

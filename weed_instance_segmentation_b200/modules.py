@@ -1,0 +1,216 @@
+"""Host-side mirrors of the pixel-decoder modules that sit on the hot path.
+
+* :class:`MSDeformAttn` mirrors ``Mask2FormerPixelDecoderEncoderMultiscaleDeformableAttention``
+  (M2F:888-983): same parameter names (``sampling_offsets``, ``attention_weights``, ``value_proj``,
+  ``output_proj``), same ``forward`` signature and return value, same ``ValueError`` on a bad
+  ``reference_points`` last dim (M2F:978) and on ``embed_dim % num_heads`` (M2F:895-898).
+* :class:`EncoderLayer` mirrors ``Mask2FormerPixelDecoderEncoderLayer`` (M2F:986-1072).
+* :func:`convert_pixel_decoder` swaps both into a loaded HF model in place, re-using the
+  existing ``nn.Parameter`` objects, so ``state_dict()`` keys, ``save_pretrained`` /
+  ``from_pretrained`` (``/root/reference/models/mask2former/train.py:167-173,221-226``) and optimizer
+  param groups are unchanged.
+
+The dense projections stay on cuBLAS tensor cores (``F.linear``); everything between them --
+bilinear gather, weighting, reduction over points and levels, and the gradient scatter -- runs in
+``libmsda_b200.so``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .functional import ms_deform_attn
+
+
+class MSDeformAttn(nn.Module):
+    """Multi-scale deformable attention module over the B200 operator."""
+
+    def __init__(self, embed_dim: int, num_heads: int, n_levels: int, n_points: int):
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError(
+                f"embed_dim (d_model) must be divisible by num_heads, but got {embed_dim} and {num_heads}"
+            )
+        self.d_model = embed_dim
+        self.n_levels = n_levels
+        self.n_heads = num_heads
+        self.n_points = n_points
+        self.im2col_step = 128  # kept for attribute compatibility (M2F:908); unused
+        self.sampling_offsets = nn.Linear(embed_dim, num_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(embed_dim, num_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(embed_dim, embed_dim)
+        self.output_proj = nn.Linear(embed_dim, embed_dim)
+        # Mask2FormerPixelDecoder.forward always passes all-False padding masks (M2F:1307-1309), which
+        # makes masked_fill (M2F:948-950) a full-tensor no-op; convert_pixel_decoder() sets this to skip it.
+        self.assume_no_padding = False
+
+    @classmethod
+    def from_hf(cls, mod: nn.Module) -> "MSDeformAttn":
+        """Wrap an HF module, sharing (not copying) its parameters."""
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.d_model, new.n_levels, new.n_heads, new.n_points = mod.d_model, mod.n_levels, mod.n_heads, mod.n_points
+        new.im2col_step = getattr(mod, "im2col_step", 128)
+        new.sampling_offsets = mod.sampling_offsets
+        new.attention_weights = mod.attention_weights
+        new.value_proj = mod.value_proj
+        new.output_proj = mod.output_proj
+        new.assume_no_padding = False
+        new.train(mod.training)
+        return new
+
+    @staticmethod
+    def with_pos_embed(tensor, position_embeddings):
+        return tensor if position_embeddings is None else tensor + position_embeddings
+
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        attention_mask: torch.Tensor | None = None,
+        encoder_hidden_states=None,
+        encoder_attention_mask=None,
+        position_embeddings: torch.Tensor | None = None,
+        reference_points=None,
+        spatial_shapes_list=None,
+        level_start_index=None,
+        output_attentions: bool = False,
+    ):
+        if position_embeddings is not None:
+            hidden_states = self.with_pos_embed(hidden_states, position_embeddings)
+        batch_size, num_queries, _ = hidden_states.shape
+        batch_size, sequence_length, _ = encoder_hidden_states.shape
+        total_elements = sum(height * width for height, width in spatial_shapes_list)
+        if total_elements != sequence_length:
+            raise ValueError(
+                "Make sure to align the spatial shapes with the sequence length of the encoder hidden states"
+            )
+        H, L, P = self.n_heads, self.n_levels, self.n_points
+
+        value = self.value_proj(encoder_hidden_states)
+        if attention_mask is not None and not self.assume_no_padding:
+            value = value.masked_fill(attention_mask[..., None], float(0))
+        value = value.view(batch_size, sequence_length, H, self.d_model // H)
+        sampling_offsets = self.sampling_offsets(hidden_states).view(batch_size, num_queries, H, L, P, 2)
+        attention_weights = self.attention_weights(hidden_states).view(batch_size, num_queries, H, L * P)
+        attention_weights = F.softmax(attention_weights, -1).view(batch_size, num_queries, H, L, P)
+        if reference_points.shape[-1] == 2:
+            offset_normalizer = torch.tensor(
+                [[shape[1], shape[0]] for shape in spatial_shapes_list],
+                dtype=reference_points.dtype, device=reference_points.device,
+            )
+            sampling_locations = (
+                reference_points[:, :, None, :, None, :]
+                + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
+            )
+        elif reference_points.shape[-1] == 4:
+            sampling_locations = (
+                reference_points[:, :, None, :, None, :2]
+                + sampling_offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+            )
+        else:
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {reference_points.shape[-1]}")
+
+        output = ms_deform_attn(value, spatial_shapes_list, level_start_index, sampling_locations, attention_weights)
+        output = self.output_proj(output)
+        return output, attention_weights
+
+
+class EncoderLayer(nn.Module):
+    """Pixel-decoder encoder layer: MSDeformAttn -> +res -> LN -> FFN -> +res -> LN (M2F:1005-1072)."""
+
+    def __init__(self, embed_dim: int = 256, num_heads: int = 8, ffn_dim: int = 1024, dropout: float = 0.0,
+                 n_levels: int = 3, n_points: int = 4):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.self_attn = MSDeformAttn(embed_dim, num_heads, n_levels, n_points)
+        self.self_attn_layer_norm = nn.LayerNorm(embed_dim)
+        self.dropout = dropout
+        self.activation_fn = F.relu
+        self.activation_dropout = dropout
+        self.fc1 = nn.Linear(embed_dim, ffn_dim)
+        self.fc2 = nn.Linear(ffn_dim, embed_dim)
+        self.final_layer_norm = nn.LayerNorm(embed_dim)
+
+    @classmethod
+    def from_hf(cls, layer: nn.Module) -> "EncoderLayer":
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.embed_dim = layer.embed_dim
+        sa = layer.self_attn
+        new.self_attn = sa if isinstance(sa, MSDeformAttn) else MSDeformAttn.from_hf(sa)
+        new.self_attn_layer_norm = layer.self_attn_layer_norm
+        new.dropout = layer.dropout
+        new.activation_fn = layer.activation_fn
+        new.activation_dropout = layer.activation_dropout
+        new.fc1, new.fc2 = layer.fc1, layer.fc2
+        new.final_layer_norm = layer.final_layer_norm
+        new.train(layer.training)
+        return new
+
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        attention_mask: torch.Tensor,
+        position_embeddings: torch.Tensor | None = None,
+        reference_points=None,
+        spatial_shapes_list=None,
+        level_start_index=None,
+        output_attentions: bool = False,
+    ):
+        residual = hidden_states
+        hidden_states, attn_weights = self.self_attn(
+            hidden_states=hidden_states,
+            attention_mask=attention_mask,
+            encoder_hidden_states=hidden_states,
+            encoder_attention_mask=attention_mask,
+            position_embeddings=position_embeddings,
+            reference_points=reference_points,
+            spatial_shapes_list=spatial_shapes_list,
+            level_start_index=level_start_index,
+            output_attentions=output_attentions,
+        )
+        hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = self.self_attn_layer_norm(residual + hidden_states)
+
+        residual = hidden_states
+        hidden_states = self.activation_fn(self.fc1(hidden_states))
+        hidden_states = F.dropout(hidden_states, p=self.activation_dropout, training=self.training)
+        hidden_states = self.fc2(hidden_states)
+        hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
+        hidden_states = self.final_layer_norm(residual + hidden_states)
+
+        if self.training:
+            # The reference clamps only `if not torch.isfinite(hidden_states).all()` (M2F:1062-1065), a
+            # device->host sync per layer per step. The clamp bounds are finfo.max - 1000, so for finite
+            # inputs it is the identity and NaN passes through unchanged: applying it unconditionally
+            # gives the same tensor without stalling the stream.
+            clamp_value = torch.finfo(hidden_states.dtype).max - 1000
+            hidden_states = torch.clamp(hidden_states, min=-clamp_value, max=clamp_value)
+
+        outputs = (hidden_states,)
+        if output_attentions:
+            outputs += (attn_weights.transpose(1, 0),)
+        return outputs
+
+
+def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True) -> int:
+    """Replace every HF pixel-decoder encoder layer (and its MSDeformAttn) inside ``model`` by the
+    mirrors above, sharing parameters. Returns the number of layers converted.
+
+    ``model`` is what ``/root/reference/models/model_utils.py:13-14`` returns
+    (``Mask2FormerForUniversalSegmentation``) or any sub-module of it.
+    """
+    from transformers.models.mask2former import modeling_mask2former as m2f
+
+    converted = 0
+    for module in model.modules():
+        if isinstance(module, m2f.Mask2FormerPixelDecoderEncoderOnly):
+            for i, layer in enumerate(module.layers):
+                if isinstance(layer, EncoderLayer):
+                    continue
+                new = EncoderLayer.from_hf(layer)
+                new.self_attn.assume_no_padding = assume_no_padding
+                module.layers[i] = new
+                converted += 1
+    return converted

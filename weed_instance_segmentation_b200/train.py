@@ -1,0 +1,219 @@
+"""Data-parallel training step around the B200 MSDeformAttn path.
+
+Re-hosts the reference's training step (``/root/reference/models/mask2former/train.py:191-205``:
+forward, ``loss / GRADIENT_ACCUMULATION``, backward, ``AdamW`` step every
+``GRADIENT_ACCUMULATION`` micro-batches) as one process per GPU with
+``torch.distributed`` (NCCL over NVLink). The path shards by image, so the only collective is
+the bucketed gradient all-reduce that ``DistributedDataParallel`` overlaps with backward, plus a
+4-byte all-reduce of ``num_masks`` (M2F:785-793) so that the DDP loss equals the single-process
+loss on the same global batch.
+
+Differences from the reference step that do not change results:
+* ``loss.item()`` (train.py:204, a device->host sync every micro-batch) is replaced by an on-device
+  running sum read once per logging interval;
+* the first micro-batch of each accumulation window runs under ``no_sync()``.
+
+There is no network here, so models are random-init from a config (the reference loads
+``facebook/mask2former-swin-large-coco-instance``, ``/root/reference/config.py:4``) and batches are
+synthetic (``synth.collate_batch``).
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import hf_patch, modules, synth
+
+# /root/reference/config.py:5-8
+LEARNING_RATE = 5e-5
+GRADIENT_ACCUMULATION = 2
+
+BACKBONES = {
+    # Swin-T / Swin-B / Swin-L shapes (the pixel-decoder MSDA dimensions do not depend on the backbone)
+    "swin_t": dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7),
+    "swin_b": dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=12),
+    "swin_l": dict(embed_dim=192, depths=[2, 2, 18, 2], num_heads=[6, 12, 24, 48], window_size=12),
+    "swin_tiny_test": dict(embed_dim=24, depths=[1, 1, 1, 1], num_heads=[1, 2, 4, 8], window_size=4),
+}
+
+
+def build_model(backbone: str = "swin_t", num_labels: int = 3, seed: int = 0, **config_overrides):
+    """Random-init ``Mask2FormerForUniversalSegmentation`` of the reference's architecture."""
+    from transformers import Mask2FormerConfig, Mask2FormerForUniversalSegmentation, SwinConfig
+
+    torch.manual_seed(seed)
+    bb = SwinConfig(out_features=["stage1", "stage2", "stage3", "stage4"], **BACKBONES[backbone])
+    cfg = Mask2FormerConfig(backbone_config=bb, num_labels=num_labels, **config_overrides)
+    return Mask2FormerForUniversalSegmentation(cfg)
+
+
+def use_b200_path(model, mode: str = "modules") -> None:
+    """Route the model's pixel-decoder MSDeformAttn through libmsda_b200.so.
+
+    ``mode="function"`` rebinds the module-global function only (M2F:980); ``mode="modules"`` also
+    swaps the encoder layers for the mirrors in ``modules.py`` (drops the per-layer isfinite sync).
+    """
+    hf_patch.install()
+    if mode == "modules":
+        modules.convert_pixel_decoder(model)
+
+
+def install_distributed_num_masks() -> None:
+    """All-reduce ``num_masks`` over the process group (what M2F:787-793 does through ``accelerate``)."""
+    from transformers.models.mask2former import modeling_mask2former as m2f
+
+    if getattr(m2f.Mask2FormerLoss.get_num_masks, "_b200_dist", False):
+        return
+
+    def get_num_masks(self, class_labels, device):
+        num_masks = sum(len(classes) for classes in class_labels)
+        num_masks = torch.as_tensor(num_masks, dtype=torch.float, device=device)
+        world = 1
+        if dist.is_available() and dist.is_initialized():
+            dist.all_reduce(num_masks)
+            world = dist.get_world_size()
+        return torch.clamp(num_masks / world, min=1)
+
+    get_num_masks._b200_dist = True
+    m2f.Mask2FormerLoss.get_num_masks = get_num_masks
+
+
+class Trainer:
+    """The reference's step loop, one process per GPU."""
+
+    def __init__(self, model, device, lr: float = LEARNING_RATE, grad_accum: int = GRADIENT_ACCUMULATION,
+                 amp_dtype: torch.dtype | None = None, ddp: bool | None = None):
+        self.device = torch.device(device)
+        self.model = model.to(self.device)
+        self.model.train()
+        self.grad_accum = grad_accum
+        self.amp_dtype = amp_dtype
+        ddp = (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) if ddp is None else ddp
+        if ddp:
+            install_distributed_num_masks()
+            kw = dict(device_ids=[self.device.index]) if self.device.type == "cuda" else {}
+            self.net = torch.nn.parallel.DistributedDataParallel(
+                self.model, gradient_as_bucket_view=True, find_unused_parameters=False, **kw)
+        else:
+            self.net = self.model
+        self.optimizer = torch.optim.AdamW(self.model.parameters(), lr=lr)  # train.py:174
+        self.micro = 0
+        self.loss_sum = torch.zeros((), device=self.device)
+        self.loss_count = 0
+
+    def step(self, batch: dict) -> torch.Tensor:
+        """One micro-batch: train.py:192-202. Returns the (undivided) loss tensor, still on device."""
+        pixel_values = batch["pixel_values"].to(self.device, non_blocking=True)
+        mask_labels = [m.to(self.device, non_blocking=True) for m in batch["mask_labels"]]
+        class_labels = [c.to(self.device, non_blocking=True) for c in batch["class_labels"]]
+        last = (self.micro + 1) % self.grad_accum == 0
+        sync_ctx = contextlib.nullcontext() if (last or self.net is self.model) else self.net.no_sync()
+        amp = (torch.autocast(self.device.type, dtype=self.amp_dtype) if self.amp_dtype is not None
+               else contextlib.nullcontext())
+        with sync_ctx:
+            with amp:
+                outputs = self.net(pixel_values=pixel_values, mask_labels=mask_labels, class_labels=class_labels)
+            (outputs.loss / self.grad_accum).backward()
+        if last:
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+        self.micro += 1
+        loss = outputs.loss.detach().reshape(())
+        self.loss_sum += loss
+        self.loss_count += 1
+        return loss
+
+    def mean_loss(self) -> float:
+        """Average loss since the last call (one device->host sync)."""
+        v = float(self.loss_sum.item()) / max(self.loss_count, 1)
+        self.loss_sum.zero_()
+        self.loss_count = 0
+        return v
+
+
+def throughput(trainer: Trainer, batches: list, steps: int, warmup: int) -> float:
+    """Seconds for ``steps`` micro-batches after ``warmup`` (device-timed on CUDA, barrier on both sides)."""
+    cuda = trainer.device.type == "cuda"
+    multi = dist.is_available() and dist.is_initialized()
+    for i in range(warmup):
+        trainer.step(batches[i % len(batches)])
+    if cuda:
+        torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    if cuda:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        trainer.step(batches[i % len(batches)])
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize()
+        secs = e0.elapsed_time(e1) / 1e3
+    else:
+        secs = time.perf_counter() - t0
+    if multi:
+        dist.barrier()
+        t = torch.tensor([secs], dtype=torch.float64, device=trainer.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    return secs
+
+
+def main(argv=None):
+    import argparse
+    import json
+
+    ap = argparse.ArgumentParser(description="Synthetic Mask2Former fine-tune step benchmark (BASELINE config 3/4)")
+    ap.add_argument("--backbone", default="swin_t", choices=sorted(BACKBONES))
+    ap.add_argument("--height", type=int, default=966)
+    ap.add_argument("--width", type=int, default=1296)
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per micro-batch")
+    ap.add_argument("--classes", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--impl", choices=["b200", "b200-function", "reference"], default="b200")
+    ap.add_argument("--amp", choices=["none", "bf16"], default="none")
+    args = ap.parse_args(argv)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local) if torch.cuda.is_available() else torch.device("cpu")
+    if device.type == "cuda":
+        torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl" if device.type == "cuda" else "gloo",
+                                **({"device_id": device} if device.type == "cuda" else {}))
+    model = build_model(args.backbone, num_labels=args.classes, seed=0)
+    if args.impl == "b200":
+        use_b200_path(model, "modules")
+    elif args.impl == "b200-function":
+        use_b200_path(model, "function")
+    trainer = Trainer(model, device, amp_dtype=torch.bfloat16 if args.amp == "bf16" else None)
+    batches = [synth.collate_batch(args.batch, args.height, args.width, num_classes=args.classes, seed=1000 * rank + i)
+               for i in range(2)]
+    secs = throughput(trainer, batches, args.steps, args.warmup)
+    loss = trainer.mean_loss()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "mask2former_train_throughput", "value": world * args.batch * args.steps / secs, "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "impl": args.impl, "loss": loss, "scaling": "weak", "data": "synthetic",
+            "dtype": "bf16 autocast" if args.amp == "bf16" else "f32",
+            "config": {"workload": f"Mask2Former {args.backbone} fine-tune step, {args.height}x{args.width}, "
+                                   f"{args.classes} classes, batch {args.batch}/GPU, AdamW lr {LEARNING_RATE}, "
+                                   f"grad accumulation {GRADIENT_ACCUMULATION}"},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
