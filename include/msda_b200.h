@@ -123,7 +123,7 @@ int msda_b200_backward(const msda_b200_desc* desc, const void* value /*dev*/, co
 #define MSDA_B200_PROF_COUNT 4
 int msda_b200_profile_ms(int which, float* ms);
 
-/* Number of kernels the library launched on this thread since the last reset (memsets not counted). */
+/* Number of kernels the library launched in this process since the last reset (memsets not counted). */
 int64_t msda_b200_launch_count(int reset);
 
 #ifdef __cplusplus

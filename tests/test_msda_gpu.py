@@ -47,9 +47,28 @@ def _oracle(value, shapes, loc, attn, grad_out, level_start=None, dtype=np.float
     return out, gv, gl, ga
 
 
-def _assert_close(got, want, bar, tag):
+def _kink_safe(loc, shapes, eps=1e-3):
+    """Samples whose pixel coordinates are at least `eps` px away from a grid line.
+
+    Bilinear sampling is continuous but not differentiable where px or py is an integer, so d/d(loc)
+    jumps there and which side a sample falls on depends on the last bit of the coordinate arithmetic
+    (fp32 in the kernel and in the reference, fp64 in the high-precision oracle). grad_loc is compared
+    on the other samples when the two sides evaluate coordinates in different precision; out,
+    grad_value and grad_attn are continuous and always compared everywhere."""
+    loc = np.asarray(loc, dtype=np.float64)
+    wh = np.asarray([[w, h] for h, w in shapes], dtype=np.float64)[None, None, None, :, None, :]
+    pix = loc * wh - 0.5
+    with np.errstate(invalid="ignore"):
+        d = np.abs(pix - np.round(pix))
+    return (np.nan_to_num(d, nan=1.0) > eps).all(-1)
+
+
+def _assert_close(got, want, bar, tag, safe=None):
     for name, g, w in zip(("out", "grad_value", "grad_loc", "grad_attn"), got, want):
         assert g.shape == w.shape, (tag, name)
+        if name == "grad_loc" and safe is not None:
+            assert safe.mean() > 0.98, "kink mask should only drop a sliver of the samples"
+            g, w = g * safe[..., None], w * safe[..., None]
         e = rel_err(g, w)
         assert e <= bar, f"{tag}: {name} rel err {e:.3e} > {bar:g}"
 
@@ -78,7 +97,7 @@ def test_golden_bf16(wis, golden):
     loc = torch.from_numpy(g["loc"])
     got = _run(wis, value, shapes, loc, attn, go)
     want = _oracle(value, shapes, loc, attn, go)  # oracle on the bf16-rounded inputs, fp64 arithmetic
-    _assert_close(got, want, BF16_BAR, name)
+    _assert_close(got, want, BF16_BAR, name, safe=_kink_safe(loc.numpy(), shapes))
 
 
 # ---------------------------------------------------------------------------- seeded random cases
@@ -103,7 +122,8 @@ def test_random_fp32(wis, case, dist):
     args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
     got = _run(wis, *args)
     _assert_close(got, _oracle(*args, dtype=np.float32), FP32_BAR, f"{tag}/{dist}")
-    _assert_close(got, _oracle(*args), 4 * FP32_BAR, f"{tag}/{dist} vs fp64")
+    _assert_close(got, _oracle(*args), 4 * FP32_BAR, f"{tag}/{dist} vs fp64",
+                  safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
 
 
 @pytest.mark.parametrize("attn_dtype", [torch.bfloat16, torch.float32], ids=["attn_bf16", "attn_f32"])
@@ -115,7 +135,8 @@ def test_random_bf16(wis, case, dist, attn_dtype):
     x = msda_inputs(B, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=8, num_queries=Q,
                     value_dtype=torch.bfloat16, attn_dtype=attn_dtype)
     args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
-    _assert_close(_run(wis, *args), _oracle(*args), BF16_BAR, f"{tag}/{dist}")
+    _assert_close(_run(wis, *args), _oracle(*args), BF16_BAR, f"{tag}/{dist}",
+                  safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
 
 
 def test_query_order_does_not_change_results(wis, monkeypatch):
@@ -124,6 +145,7 @@ def test_query_order_does_not_change_results(wis, monkeypatch):
     shapes = [(7, 9), (13, 18)]
     x = msda_inputs(2, shapes, dist="trained", seed=5)
     args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    monkeypatch.setattr(F, "_USE_ORDER", True)
     with_order = _run(wis, *args)
     monkeypatch.setattr(F, "_USE_ORDER", False)
     without = _run(wis, *args)
@@ -249,8 +271,11 @@ def test_full_size_matches_reference_on_gpu_bf16(wis):
         ra = a.detach()[sl].float().requires_grad_(True)
         ro = hf_forward_torch(rv, shapes, rl, ra)
         ro.backward(x["grad_out"][sl].float())
+        wh = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float64, device="cuda")[None, None, None, :, None, :]
+        pix = lo.detach()[sl].double() * wh - 0.5
+        safe = ((pix - pix.round()).abs() > 1e-3).all(-1, keepdim=True).float()  # see _kink_safe
         for name, got, want in (("out", out.detach()[sl], ro.detach()), ("grad_value", v.grad[sl], rv.grad),
-                                ("grad_loc", lo.grad[sl], rl.grad), ("grad_attn", a.grad[sl], ra.grad)):
+                                ("grad_loc", lo.grad[sl] * safe, rl.grad * safe), ("grad_attn", a.grad[sl], ra.grad)):
             e = ((got.float() - want).abs().max() / want.abs().max()).item()
             assert e <= BF16_BAR, f"batch {b0}: {name} rel err {e:.3e}"
         del rv, rl, ra, ro

@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -85,6 +86,7 @@ __device__ __forceinline__ Axis axis_setup(float coord, int n) {
   a.g0 = (shift == 0) ? d0 : ((shift == -1) ? d1 : 0.f);
   a.s1 = (shift == 0) ? w1 : ((shift == 1) ? w0 : 0.f);
   a.g1 = (shift == 0) ? d1 : ((shift == 1) ? d0 : 0.f);
+  if (!a.ok) a.s0 = a.s1 = a.g0 = a.g1 = 0.f;  // NaN / far outside: contributes exactly zero (0 * NaN would not)
   return a;
 }
 
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(256) msda_cvt_f32_bf16_kernel(const float4* __
 // Host side
 // ---------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};  // process-wide: autograd runs backward on its own thread
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -641,9 +643,7 @@ int msda_b200_profile_ms(int which, float* ms) {
 }
 
 int64_t msda_b200_launch_count(int reset) {
-  const long long n = g_launches;
-  if (reset) g_launches = 0;
-  return n;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 }  // extern "C"

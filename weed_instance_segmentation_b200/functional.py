@@ -29,7 +29,9 @@ _DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
 
 # Scheduling knobs (results never depend on them).
 _TILE = int(os.environ.get("MSDA_B200_TILE", "8"))            # 2-D query tile edge for the query order
-_USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "1") != "0"
+# measured on B200 (profiles/r01_notes.md): the kernels are LSU-bound and L2 absorbs the footprint, so the
+# 2-D query order buys nothing; it stays available for experiments.
+_USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "0") != "0"
 _BF16_ATOMICS = os.environ.get("MSDA_B200_BF16_ATOMICS", "0") == "1"
 
 _order_cache: dict = {}
