@@ -63,6 +63,8 @@ extern "C" {
 #define MSDA_B200_FLAG_PROFILE 1u        /* record CUDA events around each kernel (see below)    */
 #define MSDA_B200_FLAG_BF16_ATOMICS 2u   /* backward, bf16: accumulate grad_value with packed    */
                                          /* bf16x2 atomics in place (no fp32 workspace, lossy)   */
+#define MSDA_B200_FLAG_BWD_V1 4u         /* backward: force the per-corner reduction kernel (v1)  */
+                                         /* instead of the pixel-sorted kernel (v2, D=32 & P=4)  */
 
 /* Problem description: plain old data, filled by the caller on the host. */
 typedef struct msda_b200_desc {

@@ -367,6 +367,8 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
   }
 }
 
+#include "msda_bwd_sorted.cuh"
+
 // fp32 accumulator -> bf16 grad_value, 8 elements per thread
 __global__ void __launch_bounds__(256) msda_cvt_f32_bf16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst,
                                                                long long n8) {
@@ -540,8 +542,39 @@ int dispatch_fwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
   return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim %d", d->D);
 }
 
+// Backward v2 (msda_bwd_sorted.cuh): instantiated for the model's geometry (D = 32, P = 4).
+constexpr int kSortNT = 256, kSortTQ = 128, kSortCAP = 2048;
+
+bool sorted_applicable(const msda_b200_desc* d) {
+  if (d->flags & MSDA_B200_FLAG_BWD_V1) return false;
+  if (d->D != 32 || d->P != 4) return false;
+  for (int l = 0; l < d->L; ++l)
+    if (d->spatial_shapes_hw[2 * l] > 32767 || d->spatial_shapes_hw[2 * l + 1] > 32767) return false;
+  return true;
+}
+
+template <typename VT, typename AT, int ACC>
+int launch_bwd_sorted(const msda_b200_desc* d, KParams p, cudaStream_t st) {
+  constexpr int D = 32, P = 4;
+  constexpr int LPP = D / Vec16<VT>::N;
+  fill_geometry(d, p, kSortTQ);
+  const size_t smem = sorted_smem_layout<kSortNT, kSortTQ, P, kSortCAP, LPP>().total;
+  auto kern = msda_bwd_sorted_kernel<VT, AT, D, kSortNT, kSortTQ, P, kSortCAP, ACC>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
+  const long long blocks = (long long)p.B * p.num_tiles * p.H;
+  if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "backward: grid too large");
+  {
+    ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_BWD_MAIN, st);
+    kern<<<(unsigned)blocks, kSortNT, smem, st>>>(p);
+    ++g_launches;
+  }
+  return check_launch("msda_b200_backward (sorted)");
+}
+
 template <typename VT, typename AT, int ACC>
 int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
+  if (sorted_applicable(d)) return launch_bwd_sorted<VT, AT, ACC>(d, p, st);
   switch (d->D) {
     case 8: return launch_bwd<VT, AT, 8, ACC>(d, p, st);
     case 128: return launch_bwd<VT, AT, 128, ACC>(d, p, st);

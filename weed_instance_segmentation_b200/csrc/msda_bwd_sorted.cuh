@@ -1,0 +1,379 @@
+// msda_bwd_sorted.cuh -- backward v2: pixel-sorted accumulation ("level-sorted accumulation" of the north star).
+// Included by msda_b200.cu inside its anonymous namespace (uses KParams, Level, Axis, Vec16, red_add_*).
+//
+// Why: v1 issues one fp32 reduction per bilinear corner (66 M corners x 128 B at BASELINE config 2) and is bound
+// by L2 reduction throughput (measured 6.2 TB/s); shared-memory fp32 atomics are a CAS loop on sm_100a, so the
+// aggregation on chip is done by *ownership* instead:
+//
+//   per thread block = (batch, head, tile of TQ queries), per level:
+//     a  sample descriptors (slot weights, derivative codes, clamped base pixel) -> shared memory; bounding box
+//        of the touched pixels with warp reductions + native integer shared atomics
+//     b  window = bounding box (or a CAP-pixel rectangle around the mean if the box is larger)
+//     c  histogram of the TQ*P*4 corner contributions over window pixels (ATOMS.ADD, integer)
+//     d  block-wide exclusive scan -> segment starts
+//     e  fill: contributions sorted by target pixel (counting sort), 8-byte entries {pixel | id, weight}
+//     f  pull: lane groups walk equal shares of the sorted list; per entry one LDS.128 of the staged grad_out
+//        row, FMA into a register accumulator (grad_value) and a dot product with the pixel's value row
+//        (for grad_loc / grad_attn); ONE reduction to global memory per run of equal pixels, and the value row
+//        is read once per run instead of once per corner
+//     g  contributions outside the window take the v1 route (direct reduction), so any input is handled
+//     h  one thread per sample folds its four dots into grad_attn / grad_loc
+//
+// Results are identical to v1 up to fp32 summation order.
+
+template <int P>
+struct Log2P;
+template <> struct Log2P<1> { static constexpr int v = 0; };
+template <> struct Log2P<2> { static constexpr int v = 1; };
+template <> struct Log2P<4> { static constexpr int v = 2; };
+template <> struct Log2P<8> { static constexpr int v = 3; };
+
+struct SortedSmem {
+  // byte offsets into dynamic shared memory
+  size_t w, ent, dot, a, xy, gc, go, cnt, fb, misc, total;
+};
+
+template <int NT, int TQ, int P, int CAP, int LPP>
+__host__ __device__ inline SortedSmem sorted_smem_layout() {
+  constexpr int NS = TQ * P, NC = NS * 4;
+  SortedSmem s;
+  size_t o = 0;
+  s.w = o;    o += sizeof(float4) * NS;
+  s.go = o;   o += sizeof(uint4) * TQ * LPP;
+  s.ent = o;  o += sizeof(int2) * NC;
+  s.dot = o;  o += sizeof(float) * NC;
+  s.a = o;    o += sizeof(float) * NS;
+  s.xy = o;   o += sizeof(int) * NS;
+  s.gc = o;   o += sizeof(int) * NS;
+  s.cnt = o;  o += sizeof(int) * (CAP + 4);
+  s.fb = o;   o += sizeof(unsigned short) * NC;
+  o = (o + 15) & ~size_t(15);
+  s.misc = o; o += sizeof(int) * 64;
+  s.total = o;
+  return s;
+}
+
+// misc slots
+enum { MI_MINX = 0, MI_MAXX, MI_MINY, MI_MAXY, MI_SUMX, MI_SUMY, MI_NACT, MI_FBN, MI_TOTAL, MI_WSUM = 16 };
+
+__device__ __forceinline__ float gdec(int code, int k) { return (float)(((code >> (2 * k)) & 3) - 1); }
+
+template <typename VT, typename AT, int D, int NT, int TQ, int P, int CAP, int ACC>
+__global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_constant__ KParams p) {
+  constexpr int VEC = Vec16<VT>::N;
+  constexpr int LPP = D / VEC;
+  constexpr int G = NT / LPP;
+  constexpr int NS = TQ * P, NC = NS * 4;
+  constexpr int LP2 = Log2P<P>::v;
+  constexpr int WMAX = 256;  // window edge limit (8 bits per coordinate in the sort key)
+  static_assert(CAP % NT == 0 && (CAP / NT) % 4 == 0, "scan assumes CAP/NT is a multiple of 4");
+  static_assert(NC <= 65536, "entry ids are 16 bit");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SortedSmem lay = sorted_smem_layout<NT, TQ, P, CAP, LPP>();
+  float4* s_w = reinterpret_cast<float4*>(smem_raw + lay.w);
+  uint4* s_go = reinterpret_cast<uint4*>(smem_raw + lay.go);
+  int2* s_ent = reinterpret_cast<int2*>(smem_raw + lay.ent);
+  float* s_dot = reinterpret_cast<float*>(smem_raw + lay.dot);
+  float* s_a = reinterpret_cast<float*>(smem_raw + lay.a);
+  int* s_xy = reinterpret_cast<int*>(smem_raw + lay.xy);
+  int* s_gc = reinterpret_cast<int*>(smem_raw + lay.gc);
+  int* s_cnt = reinterpret_cast<int*>(smem_raw + lay.cnt);
+  unsigned short* s_fb = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
+  int* s_misc = reinterpret_cast<int*>(smem_raw + lay.misc);
+
+  int b, tile, h;
+  decode_block(p, b, tile, h);
+  const int q0 = tile * TQ;
+  const int nq = min(TQ, p.Q - q0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid / LPP, c = tid % LPP;
+  const unsigned gmask = (LPP >= 32) ? 0xffffffffu : (((1u << LPP) - 1u) << ((lane / LPP) * LPP));
+  const uint4* vb = reinterpret_cast<const uint4*>(p.value) + (long long)b * p.batch_stride16 + c;
+  const long long acc_base = (long long)b * p.batch_stride16;
+
+  // grad_out rows of the tile, staged once (zero rows for the ragged tail)
+  for (int i = tid; i < TQ * LPP; i += NT) {
+    const int ql = i / LPP, cc = i % LPP;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ql < nq) {
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      v = ldg16(reinterpret_cast<const uint4*>(p.grad_out) + (((long long)b * p.Q + q) * p.H + h) * LPP + cc);
+    }
+    s_go[i] = v;
+  }
+
+  for (int l = 0; l < p.L; ++l) {
+    const Level lv = p.lv[l];
+    const int dxs = lv.W > 1 ? 1 : 0, dys = lv.H > 1 ? 1 : 0;
+    if (tid < 16) {
+      int init = 0;
+      if (tid == MI_MINX || tid == MI_MINY) init = 0x7fffffff;
+      if (tid == MI_MAXX || tid == MI_MAXY) init = -1;
+      s_misc[tid] = init;
+    }
+    for (int i = tid; i < CAP + 4; i += NT) s_cnt[i] = 0;
+    __syncthreads();
+
+    // ---- a: descriptors + bounding box
+    for (int si0 = 0; si0 < NS; si0 += NT) {
+      const int si = si0 + tid;
+      const int ql = si >> LP2, pt = si & (P - 1);
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      int gcode = 0x55, xy = 0;  // code 1 == derivative 0
+      float a = 0.f;
+      bool active = false;
+      int xb = 0, yb = 0;
+      if (si < NS && ql < nq) {
+        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+        const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
+        const float2 loc = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
+        a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[gi]);
+        const Axis ax = axis_setup(loc.x, lv.W), ay = axis_setup(loc.y, lv.H);
+        if (ax.ok && ay.ok) {
+          w = make_float4(ax.s0, ax.s1, ay.s0, ay.s1);
+          gcode = ((int)ax.g0 + 1) | (((int)ax.g1 + 1) << 2) | (((int)ay.g0 + 1) << 4) | (((int)ay.g1 + 1) << 6);
+          const bool xa = ax.s0 != 0.f || ax.s1 != 0.f || ax.g0 != 0.f || ax.g1 != 0.f;
+          const bool ya = ay.s0 != 0.f || ay.s1 != 0.f || ay.g0 != 0.f || ay.g1 != 0.f;
+          active = xa && ya;
+        }
+        xb = ax.base; yb = ay.base;
+        xy = xb | (yb << 16);
+      }
+      if (si < NS) {
+        s_w[si] = w; s_a[si] = a; s_xy[si] = xy; s_gc[si] = gcode;
+      }
+      const unsigned act = __ballot_sync(0xffffffffu, active);
+      if (act) {
+        const int mnx = __reduce_min_sync(0xffffffffu, active ? xb : 0x7fffffff);
+        const int mxx = __reduce_max_sync(0xffffffffu, active ? xb + dxs : -1);
+        const int mny = __reduce_min_sync(0xffffffffu, active ? yb : 0x7fffffff);
+        const int mxy = __reduce_max_sync(0xffffffffu, active ? yb + dys : -1);
+        const int sx = __reduce_add_sync(0xffffffffu, active ? xb : 0);
+        const int sy = __reduce_add_sync(0xffffffffu, active ? yb : 0);
+        if (lane == 0) {
+          atomicMin(&s_misc[MI_MINX], mnx); atomicMax(&s_misc[MI_MAXX], mxx);
+          atomicMin(&s_misc[MI_MINY], mny); atomicMax(&s_misc[MI_MAXY], mxy);
+          atomicAdd(&s_misc[MI_SUMX], sx); atomicAdd(&s_misc[MI_SUMY], sy);
+          atomicAdd(&s_misc[MI_NACT], __popc(act));
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- b: window (every thread computes the same rectangle)
+    int x0 = 0, y0 = 0, ww = 0, wh = 0;
+    {
+      const int nact = s_misc[MI_NACT];
+      if (nact > 0) {
+        const int mnx = s_misc[MI_MINX], mxx = s_misc[MI_MAXX], mny = s_misc[MI_MINY], mxy = s_misc[MI_MAXY];
+        const int bw = mxx - mnx + 1, bh = mxy - mny + 1;
+        if (bw <= WMAX && bh <= WMAX && bw * bh <= CAP) {
+          x0 = mnx; y0 = mny; ww = bw; wh = bh;
+        } else {
+          ww = min(bw, 64);
+          wh = min(min(bh, CAP / ww), WMAX);
+          const int cx = s_misc[MI_SUMX] / nact, cy = s_misc[MI_SUMY] / nact;
+          x0 = min(max(cx - ww / 2, mnx), mxx - ww + 1);
+          y0 = min(max(cy - wh / 2, mny), mxy - wh + 1);
+        }
+      }
+    }
+
+    // ---- c: histogram over window pixels; contributions outside the window go to the fallback list
+    for (int id = tid; id < NC; id += NT) {
+      const int si = id >> 2, cn = id & 3;
+      const float4 w = s_w[si];
+      const int gcode = s_gc[si];
+      const bool xa = ((cn & 1) ? w.y : w.x) != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
+      const bool ya = ((cn & 2) ? w.w : w.z) != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
+      if (xa && ya) {
+        const int xy = s_xy[si];
+        const int px = (xy & 0xffff) + ((cn & 1) ? dxs : 0) - x0, py = (xy >> 16) + ((cn & 2) ? dys : 0) - y0;
+        if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
+          atomicAdd(&s_cnt[py * ww + px], 1);
+        } else {
+          s_fb[atomicAdd(&s_misc[MI_FBN], 1)] = (unsigned short)id;
+        }
+      } else {
+        s_dot[id] = 0.f;
+      }
+    }
+    __syncthreads();
+
+    // ---- d: exclusive scan of s_cnt[0..CAP)
+    {
+      constexpr int PER = CAP / NT;
+      int v[PER];
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; k += 4) {
+        const int4 t = *reinterpret_cast<const int4*>(&s_cnt[tid * PER + k]);
+        v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+        sum += t.x + t.y + t.z + t.w;
+      }
+      int incl = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      if (lane == 31) s_misc[MI_WSUM + warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        const int t = lane < NT / 32 ? s_misc[MI_WSUM + lane] : 0;
+        int inc2 = t;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, inc2, off);
+          if (lane >= off) inc2 += u;
+        }
+        if (lane < NT / 32) s_misc[MI_WSUM + lane] = inc2 - t;
+        if (lane == NT / 32 - 1) s_misc[MI_TOTAL] = inc2;
+      }
+      __syncthreads();
+      int base = s_misc[MI_WSUM + warp] + incl - sum;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int t = v[k];
+        v[k] = base;
+        base += t;
+      }
+#pragma unroll
+      for (int k = 0; k < PER; k += 4)
+        *reinterpret_cast<int4*>(&s_cnt[tid * PER + k]) = make_int4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    }
+    __syncthreads();
+
+    // ---- e: fill (counting sort by window pixel)
+    for (int id = tid; id < NC; id += NT) {
+      const int si = id >> 2, cn = id & 3;
+      const float4 w = s_w[si];
+      const int gcode = s_gc[si];
+      const float wx = (cn & 1) ? w.y : w.x, wy = (cn & 2) ? w.w : w.z;
+      const bool xa = wx != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
+      const bool ya = wy != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
+      if (xa && ya) {
+        const int xy = s_xy[si];
+        const int px = (xy & 0xffff) + ((cn & 1) ? dxs : 0) - x0, py = (xy >> 16) + ((cn & 2) ? dys : 0) - y0;
+        if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
+          const int slot = atomicAdd(&s_cnt[py * ww + px], 1);
+          s_ent[slot] = make_int2((py << 24) | (px << 16) | id, __float_as_int(s_a[si] * wy * wx));
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- f: pull over the sorted list, equal shares per lane group
+    {
+      const int E = s_misc[MI_TOTAL];
+      const int e0 = (int)(((long long)g * E) / G), e1 = (int)(((long long)(g + 1) * E) / G);
+      int cur = -1;
+      long long cur_off = 0;
+      float acc[VEC], vf[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; vf[j] = 0.f; }
+      for (int e = e0; e < e1; ++e) {
+        const int2 en = s_ent[e];
+        const int pix = (int)((unsigned)en.x >> 16);
+        const int id = en.x & 0xffff;
+        const float wgt = __int_as_float(en.y);
+        if (pix != cur) {
+          if (cur >= 0) {
+            if (ACC == 0) {
+              float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC;
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            } else {
+              const uint4 pk = Vec16<VT>::pack(acc);
+              red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC, pk.x, pk.y, pk.z, pk.w);
+            }
+          }
+          cur = pix;
+          const int px = pix & 0xff, py = pix >> 8;
+          cur_off = (long long)((lv.start + (y0 + py) * lv.W + (x0 + px)) * p.H + h) * LPP;
+          Vec16<VT>::unpack(ldg16(vb + cur_off), vf);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        }
+        float gf[VEC];
+        Vec16<VT>::unpack(s_go[(id >> (2 + LP2)) * LPP + c], gf);
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          acc[j] = fmaf(wgt, gf[j], acc[j]);
+          d = fmaf(gf[j], vf[j], d);
+        }
+#pragma unroll
+        for (int o = 1; o < LPP; o <<= 1) d += __shfl_xor_sync(gmask, d, o);
+        if (c == 0) s_dot[id] = d;
+      }
+      if (cur >= 0) {
+        if (ACC == 0) {
+          float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC;
+#pragma unroll
+          for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+          const uint4 pk = Vec16<VT>::pack(acc);
+          red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC, pk.x, pk.y, pk.z, pk.w);
+        }
+      }
+    }
+
+    // ---- g: contributions outside the window: direct reduction (v1 route)
+    {
+      const int nfb = s_misc[MI_FBN];
+      for (int k = g; k < nfb; k += G) {
+        const int id = s_fb[k];
+        const int si = id >> 2, cn = id & 3;
+        const float4 w = s_w[si];
+        const float wgt = s_a[si] * ((cn & 2) ? w.w : w.z) * ((cn & 1) ? w.y : w.x);
+        const int xy = s_xy[si];
+        const int x = (xy & 0xffff) + ((cn & 1) ? dxs : 0), y = (xy >> 16) + ((cn & 2) ? dys : 0);
+        const long long off = (long long)((lv.start + y * lv.W + x) * p.H + h) * LPP;
+        float vf[VEC], gf[VEC];
+        Vec16<VT>::unpack(ldg16(vb + off), vf);
+        Vec16<VT>::unpack(s_go[(id >> (2 + LP2)) * LPP + c], gf);
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) d = fmaf(gf[j], vf[j], d);
+#pragma unroll
+        for (int o = 1; o < LPP; o <<= 1) d += __shfl_xor_sync(gmask, d, o);
+        if (c == 0) s_dot[id] = d;
+        if (wgt != 0.f) {
+          if (ACC == 0) {
+            float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + off + c) * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4)
+              red_add_f32x4(dst + j, wgt * gf[j], wgt * gf[j + 1], wgt * gf[j + 2], wgt * gf[j + 3]);
+          } else {
+            float t[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) t[j] = wgt * gf[j];
+            const uint4 pk = Vec16<VT>::pack(t);
+            red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + off + c) * VEC, pk.x, pk.y, pk.z, pk.w);
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- h: per-sample gradients
+    for (int si = tid; si < NS; si += NT) {
+      const int ql = si >> LP2, pt = si & (P - 1);
+      if (ql >= nq) continue;
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
+      const float4 d = *reinterpret_cast<const float4*>(&s_dot[si * 4]);
+      const float4 w = s_w[si];
+      const int gcode = s_gc[si];
+      const float a = s_a[si];
+      const float gl = gdec(gcode, 0), gr = gdec(gcode, 1), gt = gdec(gcode, 2), gb = gdec(gcode, 3);
+      const float top_s = w.x * d.x + w.y * d.y, bot_s = w.x * d.z + w.y * d.w;
+      const float top_g = gl * d.x + gr * d.y, bot_g = gl * d.z + gr * d.w;
+      reinterpret_cast<AT*>(p.grad_attn)[gi] = from_float<AT>(w.z * top_s + w.w * bot_s);
+      reinterpret_cast<float2*>(p.grad_loc)[gi] =
+          make_float2((float)lv.W * a * (w.z * top_g + w.w * bot_g), (float)lv.H * a * (gt * top_s + gb * bot_s));
+    }
+    __syncthreads();
+  }
+}

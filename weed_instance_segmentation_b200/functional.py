@@ -28,11 +28,18 @@ from ._cabi import MSDAError  # noqa: F401  (re-export)
 _DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
 
 # Scheduling knobs (results never depend on them).
-_TILE = int(os.environ.get("MSDA_B200_TILE", "8"))            # 2-D query tile edge for the query order
-# measured on B200 (profiles/r01_notes.md): the kernels are LSU-bound and L2 absorbs the footprint, so the
-# 2-D query order buys nothing; it stays available for experiments.
-_USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "0") != "0"
+def _parse_tile(text):
+    parts = [int(v) for v in text.lower().split("x")]
+    return (parts[0], parts[0]) if len(parts) == 1 else (parts[0], parts[1])
+
+
+# 2-D query tile (rows x cols) of the query order. The pixel-sorted backward (csrc/msda_bwd_sorted.cuh) owns 128
+# queries per block; an 8 x 16 patch keeps their samples inside a small pixel window, which is what lets it merge
+# contributions before reducing. The forward does not care (measured: LSU-bound either way, profiles/r01_notes.md).
+_TILE = _parse_tile(os.environ.get("MSDA_B200_TILE", "8x16"))
+_USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "1") != "0"
 _BF16_ATOMICS = os.environ.get("MSDA_B200_BF16_ATOMICS", "0") == "1"
+_BWD_V1 = os.environ.get("MSDA_B200_BWD_V1", "0") == "1"
 
 _order_cache: dict = {}
 _lsi_checked: set = set()
@@ -72,13 +79,14 @@ def _level_start(shapes: Sequence[tuple[int, int]], level_start_index) -> list[i
 
 
 def query_order_2d(shapes: Sequence[tuple[int, int]], tile: int, device) -> torch.Tensor:
-    """Permutation of 0..S-1 that walks every level in ``tile x tile`` blocks (row-major inside).
+    """Permutation of 0..S-1 that walks every level in ``tile`` = (rows, cols) blocks (row-major inside).
 
     Used when ``Q == S`` (pixel-decoder self-attention: query i sits on pixel i, M2F:1117-1123):
     a thread block then owns a compact 2-D patch of queries whose samples overlap, which is what
     keeps the bilinear footprint in L1. Scheduling only; results do not depend on it.
     """
-    key = (tuple(shapes), tile, str(device))
+    th, tw = (tile, tile) if isinstance(tile, int) else tile
+    key = (tuple(shapes), th, tw, str(device))
     hit = _order_cache.get(key)
     if hit is not None:
         return hit
@@ -86,8 +94,8 @@ def query_order_2d(shapes: Sequence[tuple[int, int]], tile: int, device) -> torc
     for h, w in shapes:
         y = torch.arange(h).view(h, 1).expand(h, w)
         x = torch.arange(w).view(1, w).expand(h, w)
-        tiles_x = (w + tile - 1) // tile
-        rank = ((y // tile) * tiles_x + (x // tile)) * (tile * tile) + (y % tile) * tile + (x % tile)
+        tiles_x = (w + tw - 1) // tw
+        rank = ((y // th) * tiles_x + (x // tw)) * (th * tw) + (y % th) * tw + (x % tw)
         parts.append(start + torch.argsort(rank.reshape(-1), stable=True))
         start += h * w
     order = torch.cat(parts).to(torch.int32).to(device)
@@ -167,6 +175,8 @@ class MSDeformAttnFunction(torch.autograd.Function):
         grad_out = grad_out.to(value.dtype).contiguous()
         if _BF16_ATOMICS and value.dtype == torch.bfloat16:
             flags |= _cabi.FLAG_BF16_ATOMICS
+        if _BWD_V1:
+            flags |= _cabi.FLAG_BWD_V1
         desc, keep = _cabi.make_desc(B, S, Q, H, D, L, P, _DTYPE_CODE[value.dtype], _DTYPE_CODE[attn.dtype],
                                      shapes, level_start, flags)
         grad_value = torch.empty_like(value)
