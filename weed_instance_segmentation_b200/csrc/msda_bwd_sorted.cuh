@@ -46,7 +46,7 @@ __host__ __device__ inline SortedSmem sorted_smem_layout() {
   s.xy = o;   o += sizeof(int) * NS;
   s.gc = o;   o += sizeof(int) * NS;
   s.cnt = o;  o += sizeof(int) * (CAP + 4);
-  s.fb = o;   o += sizeof(unsigned short) * NC;
+  s.fb = s.ent + sizeof(int2) * NC;  // fallback ids grow downwards from the end of the entry array (E + nfb <= NC)
   o = (o + 15) & ~size_t(15);
   s.misc = o; o += sizeof(int) * 64;
   s.total = o;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
   int* s_xy = reinterpret_cast<int*>(smem_raw + lay.xy);
   int* s_gc = reinterpret_cast<int*>(smem_raw + lay.gc);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + lay.cnt);
-  unsigned short* s_fb = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
+  unsigned short* s_fb_end = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
   int* s_misc = reinterpret_cast<int*>(smem_raw + lay.misc);
 
   int b, tile, h;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
         if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
           atomicAdd(&s_cnt[py * ww + px], 1);
         } else {
-          s_fb[atomicAdd(&s_misc[MI_FBN], 1)] = (unsigned short)id;
+          s_fb_end[-1 - atomicAdd(&s_misc[MI_FBN], 1)] = (unsigned short)id;
         }
       } else {
         s_dot[id] = 0.f;
@@ -263,34 +263,39 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     }
     __syncthreads();
 
-    // ---- f: pull over the sorted list, equal shares per lane group
+    // ---- f: pull over the sorted list: every lane group walks `per` consecutive entries (the same trip
+    // count for all groups, so the warp stays convergent and the dot reduction can use full-mask shuffles)
     {
       const int E = s_misc[MI_TOTAL];
-      const int e0 = (int)(((long long)g * E) / G), e1 = (int)(((long long)(g + 1) * E) / G);
-      int cur = -1;
-      long long cur_off = 0;
+      const int per = (E + G - 1) / G;
+      const int e0 = g * per;
+      int cur = -1, cur_off = 0;
       float acc[VEC], vf[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; vf[j] = 0.f; }
-      for (int e = e0; e < e1; ++e) {
-        const int2 en = s_ent[e];
+      auto flush = [&]() {
+        if (ACC == 0) {
+          float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + c) * VEC + (long long)cur_off * VEC;
+#pragma unroll
+          for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+          const uint4 pk = Vec16<VT>::pack(acc);
+          red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + c) * VEC + (long long)cur_off * VEC,
+                         pk.x, pk.y, pk.z, pk.w);
+        }
+      };
+      for (int k = 0; k < per; ++k) {
+        const int e = e0 + k;
+        const bool valid = e < E;
+        int2 en = make_int2(cur << 16, 0);  // padding entry: same pixel, weight 0, dot discarded
+        if (valid) en = s_ent[e];
         const int pix = (int)((unsigned)en.x >> 16);
         const int id = en.x & 0xffff;
         const float wgt = __int_as_float(en.y);
-        if (pix != cur) {
-          if (cur >= 0) {
-            if (ACC == 0) {
-              float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC;
-#pragma unroll
-              for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            } else {
-              const uint4 pk = Vec16<VT>::pack(acc);
-              red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC, pk.x, pk.y, pk.z, pk.w);
-            }
-          }
+        if (valid && pix != cur) {
+          if (cur >= 0) flush();
           cur = pix;
-          const int px = pix & 0xff, py = pix >> 8;
-          cur_off = (long long)((lv.start + (y0 + py) * lv.W + (x0 + px)) * p.H + h) * LPP;
+          cur_off = ((lv.start + (y0 + (pix >> 8)) * lv.W + (x0 + (pix & 0xff))) * p.H + h) * LPP;
           Vec16<VT>::unpack(ldg16(vb + cur_off), vf);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -304,26 +309,17 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
           d = fmaf(gf[j], vf[j], d);
         }
 #pragma unroll
-        for (int o = 1; o < LPP; o <<= 1) d += __shfl_xor_sync(gmask, d, o);
-        if (c == 0) s_dot[id] = d;
+        for (int o = 1; o < LPP; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (valid && c == 0) s_dot[id] = d;
       }
-      if (cur >= 0) {
-        if (ACC == 0) {
-          float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC;
-#pragma unroll
-          for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        } else {
-          const uint4 pk = Vec16<VT>::pack(acc);
-          red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + cur_off + c) * VEC, pk.x, pk.y, pk.z, pk.w);
-        }
-      }
+      if (cur >= 0) flush();
     }
 
     // ---- g: contributions outside the window: direct reduction (v1 route)
     {
       const int nfb = s_misc[MI_FBN];
       for (int k = g; k < nfb; k += G) {
-        const int id = s_fb[k];
+        const int id = s_fb_end[-1 - k];
         const int si = id >> 2, cn = id & 3;
         const float4 w = s_w[si];
         const float wgt = s_a[si] * ((cn & 2) ? w.w : w.z) * ((cn & 1) ? w.y : w.x);
