@@ -102,6 +102,27 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     s_go[i] = v;
   }
 
+  // per-thread samples: si = r*NT + tid; their loc / attn are prefetched one level ahead
+  constexpr int SPT = (NS + NT - 1) / NT;
+  float2 pre_loc[SPT];
+  float pre_a[SPT];
+  auto fetch_level = [&](int l) {
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int si = r * NT + tid;
+      const int ql = si >> LP2, pt = si & (P - 1);
+      pre_loc[r] = make_float2(0.f, 0.f);
+      pre_a[r] = 0.f;
+      if (l < p.L && si < NS && ql < nq) {
+        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+        const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
+        pre_loc[r] = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
+        pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[gi]);
+      }
+    }
+  };
+  fetch_level(0);
+
   for (int l = 0; l < p.L; ++l) {
     const Level lv = p.lv[l];
     const int dxs = lv.W > 1 ? 1 : 0, dys = lv.H > 1 ? 1 : 0;
@@ -114,21 +135,19 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     for (int i = tid; i < CAP + 4; i += NT) s_cnt[i] = 0;
     __syncthreads();
 
-    // ---- a: descriptors + bounding box
-    for (int si0 = 0; si0 < NS; si0 += NT) {
-      const int si = si0 + tid;
-      const int ql = si >> LP2, pt = si & (P - 1);
+    // ---- a: descriptors + bounding box (loc / attn of this level were fetched during the previous level)
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int si = r * NT + tid;
+      const int ql = si >> LP2;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       int gcode = 0x55, xy = 0;  // code 1 == derivative 0
       float a = 0.f;
       bool active = false;
       int xb = 0, yb = 0;
       if (si < NS && ql < nq) {
-        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
-        const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
-        const float2 loc = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
-        a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[gi]);
-        const Axis ax = axis_setup(loc.x, lv.W), ay = axis_setup(loc.y, lv.H);
+        a = pre_a[r];
+        const Axis ax = axis_setup(pre_loc[r].x, lv.W), ay = axis_setup(pre_loc[r].y, lv.H);
         if (ax.ok && ay.ok) {
           w = make_float4(ax.s0, ax.s1, ay.s0, ay.s1);
           gcode = ((int)ax.g0 + 1) | (((int)ax.g1 + 1) << 2) | (((int)ay.g0 + 1) << 4) | (((int)ay.g1 + 1) << 6);
@@ -158,6 +177,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
         }
       }
     }
+    fetch_level(l + 1);  // in flight during the histogram / sort / pull of this level
     __syncthreads();
 
     // ---- b: window (every thread computes the same rectangle)
@@ -284,11 +304,20 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
                          pk.x, pk.y, pk.z, pk.w);
         }
       };
+      // software pipeline: entry k+2 and the grad_out row of entry k+1 are in flight while entry k is processed
+      constexpr int PAD = (int)0xffff0000u;  // padding entry (beyond the share or the list): weight 0, dot discarded
+      const int e_end = min(e0 + per, E);
+      auto load_entry = [&](int e) { return e < e_end ? s_ent[e] : make_int2(PAD, 0); };
+      auto go_row = [&](const int2& en) { return s_go[((en.x & 0xffff) >> (2 + LP2)) * LPP + c]; };
+      int2 en_next = load_entry(e0), en_next2 = load_entry(e0 + 1);
+      uint4 go_next = go_row(en_next);
       for (int k = 0; k < per; ++k) {
-        const int e = e0 + k;
-        const bool valid = e < E;
-        int2 en = make_int2(cur << 16, 0);  // padding entry: same pixel, weight 0, dot discarded
-        if (valid) en = s_ent[e];
+        const int2 en = en_next;
+        const uint4 go_raw = go_next;
+        en_next = en_next2;
+        en_next2 = load_entry(e0 + k + 2);
+        go_next = go_row(en_next);
+        const bool valid = en.x != PAD;
         const int pix = (int)((unsigned)en.x >> 16);
         const int id = en.x & 0xffff;
         const float wgt = __int_as_float(en.y);
@@ -301,7 +330,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
           for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
         }
         float gf[VEC];
-        Vec16<VT>::unpack(s_go[(id >> (2 + LP2)) * LPP + c], gf);
+        Vec16<VT>::unpack(go_raw, gf);
         float d = 0.f;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
