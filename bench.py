@@ -349,7 +349,9 @@ def run_b200(args, rank, world, local_rank):
     dom_ms = kern[dominant]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "msda_bwd_kernel" if dominant == "bwd_main" else "msda_fwd_kernel",
+        "bound": "hbm",
+        "kernel": ("msda_bwd_sorted_kernel" if (args.dtype == "bf16" and not (prob.flags & _cabi.FLAG_BWD_V1))
+                   else "msda_bwd_kernel") if dominant == "bwd_main" else "msda_fwd_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms, "traffic": recorded_traffic(dominant),
     }

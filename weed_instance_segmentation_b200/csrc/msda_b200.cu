@@ -24,6 +24,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 #include "msda_b200.h"
 
@@ -48,6 +49,13 @@ struct KParams {
   float* grad_loc;
   void* grad_attn;
   const int* q_order;
+  // fused prologue (M2F:952-971): raw sampling offsets and attention logits instead of loc / attn
+  const void* offsets;   // (B,Q,H,L,P,2), dtype AT
+  const void* logits;    // (B,Q,H,L*P),   dtype AT
+  const float* ref;      // (B,Q,L,2) reference points
+  float* attn_out;       // optional (B,Q,H,L,P) softmax output
+  void* grad_offsets;    // backward, dtype AT
+  void* grad_logits;     // backward, dtype AT
   int B, S, Q, H, L, P, LP;
   int num_tiles;
   long long batch_stride16;  // S*H*D*sizeof(T)/16
@@ -166,9 +174,70 @@ __device__ __forceinline__ void decode_block(const KParams& p, int& b, int& tile
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused prologue helpers (M2F:952-971): attn = softmax(logits over L*P), loc = ref + off / (W_l, H_l)
+// ---------------------------------------------------------------------------------------------
+template <typename AT>
+__device__ __forceinline__ float2 load_pair(const void* base, long long idx);
+template <>
+__device__ __forceinline__ float2 load_pair<float>(const void* base, long long idx) {
+  return __ldg(reinterpret_cast<const float2*>(base) + idx);
+}
+template <>
+__device__ __forceinline__ float2 load_pair<__nv_bfloat16>(const void* base, long long idx) {
+  const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(base)[idx];
+  return make_float2(__low2float(v), __high2float(v));
+}
+template <typename AT>
+__device__ __forceinline__ void store_pair(void* base, long long idx, float x, float y);
+template <>
+__device__ __forceinline__ void store_pair<float>(void* base, long long idx, float x, float y) {
+  reinterpret_cast<float2*>(base)[idx] = make_float2(x, y);
+}
+template <>
+__device__ __forceinline__ void store_pair<__nv_bfloat16>(void* base, long long idx, float x, float y) {
+  reinterpret_cast<__nv_bfloat162*>(base)[idx] = __floats2bfloat162_rn(x, y);
+}
+
+// si: global sample index ((b*Q+q)*H+h)*LP + s; ri: reference-point index (b*Q+q)*L + l
+template <typename AT>
+__device__ __forceinline__ float2 fused_loc(const KParams& p, long long si, long long ri, const Level& lv) {
+  const float2 off = load_pair<AT>(p.offsets, si);
+  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + ri);
+  return make_float2(__fadd_rn(r.x, __fdiv_rn(off.x, (float)lv.W)), __fadd_rn(r.y, __fdiv_rn(off.y, (float)lv.H)));
+}
+
+// max and 1 / sum(exp(x - max)) of the LP logits of one (query, head)
+template <typename AT>
+__device__ __forceinline__ void softmax_stats(const AT* lg, int LP, float& mx, float& inv) {
+  mx = -INFINITY;
+  for (int s = 0; s < LP; ++s) mx = fmaxf(mx, to_float<AT>(lg[s]));
+  float sum = 0.f;
+  for (int s = 0; s < LP; ++s) sum += expf(to_float<AT>(lg[s]) - mx);
+  inv = 1.f / sum;
+}
+
+// softmax of the tile's (query, head) rows into shared memory, one thread per query
+template <typename AT, int NT>
+__device__ __forceinline__ void tile_softmax(const KParams& p, int b, int h, int q0, int nq, float* s_att, bool write_out) {
+  const int LP = p.LP;
+  for (int ql = threadIdx.x; ql < nq; ql += NT) {
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    const long long row = (((long long)b * p.Q + q) * p.H + h) * LP;
+    const AT* lg = reinterpret_cast<const AT*>(p.logits) + row;
+    float mx, inv;
+    softmax_stats<AT>(lg, LP, mx, inv);
+    for (int s = 0; s < LP; ++s) {
+      const float a = expf(to_float<AT>(lg[s]) - mx) * inv;
+      s_att[ql * LP + s] = a;
+      if (write_out && p.attn_out) p.attn_out[row + s] = a;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
-template <typename VT, typename AT, int D, int NT, int QPG>
+template <typename VT, typename AT, int D, int NT, int QPG, bool FUSED>
 __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -176,6 +245,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* sw = reinterpret_cast<float4*>(smem_raw);                    // [LP][ROW] slot weights * attn
   int* soff = reinterpret_cast<int*>(smem_raw + (size_t)p.LP * T::ROW * sizeof(float4));  // [LP][ROW]
+  float* s_att = reinterpret_cast<float*>(soff + (size_t)p.LP * T::ROW);                  // FUSED: [TQ][LP] softmax
 
   int b, tile, h;
   decode_block(p, b, tile, h);
@@ -183,15 +253,21 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
   const int nq = min(T::TQ, p.Q - q0);
   const int LP = p.LP;
 
+  if (FUSED) {
+    tile_softmax<AT, NT>(p, b, h, q0, nq, s_att, true);
+    __syncthreads();
+  }
+
   // ---- phase 1: descriptors
   for (int i = threadIdx.x; i < nq * LP; i += NT) {
     const int ql = i / LP, s = i - ql * LP;
     const int l = s / p.P;
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
-    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Level lv = p.lv[l];
+    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, lv)
+                            : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
     const bool ok = ax.ok && ay.ok;
     const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
@@ -244,7 +320,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
 // ---------------------------------------------------------------------------------------------
 // ACC: 0 = fp32 accumulator with red.v4.f32 (grad_value itself for fp32 values, workspace for bf16)
 //      1 = bf16 grad_value accumulated in place with red.v4.bf16x2 (MSDA_B200_FLAG_BF16_ATOMICS)
-template <typename VT, typename AT, int D, int NT, int QPG, int ACC>
+template <typename VT, typename AT, int D, int NT, int QPG, int ACC, bool FUSED>
 __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -257,11 +333,18 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
   float4* sd = sg + n;                                  // [LP][TQ][LPP] per-lane partial dots
   float* sa = reinterpret_cast<float*>(sd + (size_t)LP * T::TQ * LPP);  // [LP][ROW] attn
   int* soff = reinterpret_cast<int*>(sa + n);           // [LP][ROW]
+  float* s_att = reinterpret_cast<float*>(soff + n);    // FUSED: [TQ][LP] softmax
+  float* s_ga = s_att + (size_t)T::TQ * LP;             // FUSED: [TQ][LP] d loss / d attn
 
   int b, tile, h;
   decode_block(p, b, tile, h);
   const int q0 = tile * T::TQ;
   const int nq = min(T::TQ, p.Q - q0);
+
+  if (FUSED) {
+    tile_softmax<AT, NT>(p, b, h, q0, nq, s_att, false);
+    __syncthreads();
+  }
 
   // ---- phase 1: descriptors
   for (int i = threadIdx.x; i < nq * LP; i += NT) {
@@ -269,9 +352,10 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
     const int l = s / p.P;
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
-    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Level lv = p.lv[l];
+    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, lv)
+                            : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
     const bool ok = ax.ok && ay.ok;
     const int k = s * T::ROW + ql;
@@ -362,8 +446,26 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
     const float g_attn = w.z * top_s + w.w * bot_s;
     const float g_px = w.z * top_g + w.w * bot_g;
     const float g_py = gw.z * top_s + gw.w * bot_s;
-    reinterpret_cast<AT*>(p.grad_attn)[si] = from_float<AT>(g_attn);
-    reinterpret_cast<float2*>(p.grad_loc)[si] = make_float2((float)p.lv[l].W * a * g_px, (float)p.lv[l].H * a * g_py);
+    if (FUSED) {
+      // loc = ref + off / (W, H)  =>  d/d off = (d/d loc) / (W, H) = attn * d sample / d pixel
+      store_pair<AT>(p.grad_offsets, si, a * g_px, a * g_py);
+      s_ga[i] = g_attn;
+    } else {
+      reinterpret_cast<AT*>(p.grad_attn)[si] = from_float<AT>(g_attn);
+      reinterpret_cast<float2*>(p.grad_loc)[si] = make_float2((float)p.lv[l].W * a * g_px, (float)p.lv[l].H * a * g_py);
+    }
+  }
+  if (FUSED) {
+    // softmax backward over the L*P logits of each (query, head): g_j = a_j * (ga_j - sum_k a_k ga_k)
+    __syncthreads();
+    for (int ql = threadIdx.x; ql < nq; ql += NT) {
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const long long row = (((long long)b * p.Q + q) * p.H + h) * LP;
+      float dotsum = 0.f;
+      for (int s = 0; s < LP; ++s) dotsum = fmaf(s_att[ql * LP + s], s_ga[ql * LP + s], dotsum);
+      for (int s = 0; s < LP; ++s)
+        reinterpret_cast<AT*>(p.grad_logits)[row + s] = from_float<AT>(s_att[ql * LP + s] * (s_ga[ql * LP + s] - dotsum));
+    }
   }
 }
 
@@ -488,13 +590,14 @@ int check_launch(const char* what) {
 constexpr int kFwdNT = 256, kFwdQPG = 1;
 constexpr int kBwdNT = 128, kBwdQPG = 1;
 
-template <typename VT, typename AT, int D>
+template <typename VT, typename AT, int D, bool FUSED>
 int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int LPP = D / Vec16<VT>::N;
   using T = Tile<kFwdNT, LPP, kFwdQPG>;
   fill_geometry(d, p, T::TQ);
-  const size_t smem = (size_t)p.LP * T::ROW * (sizeof(float4) + sizeof(int));
-  auto kern = msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG>;
+  const size_t smem = (size_t)p.LP * T::ROW * (sizeof(float4) + sizeof(int)) +
+                      (FUSED ? (size_t)T::TQ * p.LP * sizeof(float) : 0);
+  auto kern = msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG, FUSED>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
@@ -508,15 +611,16 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   return check_launch("msda_b200_forward");
 }
 
-template <typename VT, typename AT, int D, int ACC>
+template <typename VT, typename AT, int D, int ACC, bool FUSED>
 int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int LPP = D / Vec16<VT>::N;
   using T = Tile<kBwdNT, LPP, kBwdQPG>;
   fill_geometry(d, p, T::TQ);
   const size_t n = (size_t)p.LP * T::ROW;
-  const size_t smem =
-      n * (2 * sizeof(float4) + sizeof(float) + sizeof(int)) + (size_t)p.LP * T::TQ * LPP * sizeof(float4);
-  auto kern = msda_bwd_kernel<VT, AT, D, kBwdNT, kBwdQPG, ACC>;
+  const size_t smem = n * (2 * sizeof(float4) + sizeof(float) + sizeof(int)) +
+                      (size_t)p.LP * T::TQ * LPP * sizeof(float4) +
+                      (FUSED ? 2 * (size_t)T::TQ * p.LP * sizeof(float) : 0);
+  auto kern = msda_bwd_kernel<VT, AT, D, kBwdNT, kBwdQPG, ACC, FUSED>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
@@ -530,14 +634,14 @@ int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   return check_launch("msda_b200_backward");
 }
 
-template <typename VT, typename AT>
+template <typename VT, typename AT, bool FUSED>
 int dispatch_fwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
   switch (d->D) {
-    case 8: return launch_fwd<VT, AT, 8>(d, p, st);
-    case 128: return launch_fwd<VT, AT, 128>(d, p, st);
-    case 16: return launch_fwd<VT, AT, 16>(d, p, st);
-    case 32: return launch_fwd<VT, AT, 32>(d, p, st);
-    case 64: return launch_fwd<VT, AT, 64>(d, p, st);
+    case 8: return launch_fwd<VT, AT, 8, FUSED>(d, p, st);
+    case 128: return launch_fwd<VT, AT, 128, FUSED>(d, p, st);
+    case 16: return launch_fwd<VT, AT, 16, FUSED>(d, p, st);
+    case 32: return launch_fwd<VT, AT, 32, FUSED>(d, p, st);
+    case 64: return launch_fwd<VT, AT, 64, FUSED>(d, p, st);
   }
   return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim %d", d->D);
 }
@@ -550,86 +654,60 @@ bool sorted_applicable(const msda_b200_desc* d) {
   if (d->D != 32 || d->P != 4) return false;
   // fp32 rows are 8 lanes wide: half as many entries per warp step, measured slower than v1 (2.35 vs 2.12 ms)
   if (d->value_dtype != MSDA_B200_BF16) return false;
-  for (int l = 0; l < d->L; ++l)
-    if (d->spatial_shapes_hw[2 * l] > 32767 || d->spatial_shapes_hw[2 * l + 1] > 32767) return false;
+  for (int l = 0; l < d->L; ++l)  // pixel coordinates are packed into 12 bits each
+    if (d->spatial_shapes_hw[2 * l] > 4095 || d->spatial_shapes_hw[2 * l + 1] > 4095) return false;
   return true;
 }
 
-template <typename VT, typename AT, int ACC, int kSortNT, int kSortTQ>
+template <typename VT, typename AT, int ACC, bool FUSED, int kNT, int kTQ>
 int launch_bwd_sorted_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int D = 32, P = 4;
   constexpr int LPP = D / Vec16<VT>::N;
-  fill_geometry(d, p, kSortTQ);
-  const size_t smem = sorted_smem_layout<kSortNT, kSortTQ, P, kSortCAP, LPP>().total;
-  auto kern = msda_bwd_sorted_kernel<VT, AT, D, kSortNT, kSortTQ, P, kSortCAP, ACC>;
+  fill_geometry(d, p, kTQ);
+  const size_t smem = sorted_smem_layout<kNT, kTQ, P, kSortCAP, LPP>().total;
+  auto kern = msda_bwd_sorted_kernel<VT, AT, D, kNT, kTQ, P, kSortCAP, ACC, FUSED>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
   const long long blocks = (long long)p.B * p.num_tiles * p.H;
   if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "backward: grid too large");
   {
     ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_BWD_MAIN, st);
-    kern<<<(unsigned)blocks, kSortNT, smem, st>>>(p);
+    kern<<<(unsigned)blocks, kNT, smem, st>>>(p);
     ++g_launches;
   }
   return check_launch("msda_b200_backward (sorted)");
 }
 
-template <typename VT, typename AT, int ACC>
-int launch_bwd_sorted(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
-  if (d->flags & MSDA_B200_FLAG_BWD_TQ256) return launch_bwd_sorted_cfg<VT, AT, ACC, 512, 256>(d, p, st);
-  return launch_bwd_sorted_cfg<VT, AT, ACC, kSortNT, kSortTQ>(d, p, st);
-}
-
-template <typename VT, typename AT, int ACC>
+template <typename VT, typename AT, int ACC, bool FUSED>
 int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
-  if (sorted_applicable(d)) return launch_bwd_sorted<VT, AT, ACC>(d, p, st);
+  if constexpr (std::is_same<VT, __nv_bfloat16>::value) {
+    if (sorted_applicable(d)) {
+      if (d->flags & MSDA_B200_FLAG_BWD_TQ256) return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, 512, 256>(d, p, st);
+      return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, kSortNT, kSortTQ>(d, p, st);
+    }
+  }
   switch (d->D) {
-    case 8: return launch_bwd<VT, AT, 8, ACC>(d, p, st);
-    case 128: return launch_bwd<VT, AT, 128, ACC>(d, p, st);
-    case 16: return launch_bwd<VT, AT, 16, ACC>(d, p, st);
-    case 32: return launch_bwd<VT, AT, 32, ACC>(d, p, st);
-    case 64: return launch_bwd<VT, AT, 64, ACC>(d, p, st);
+    case 8: return launch_bwd<VT, AT, 8, ACC, FUSED>(d, p, st);
+    case 128: return launch_bwd<VT, AT, 128, ACC, FUSED>(d, p, st);
+    case 16: return launch_bwd<VT, AT, 16, ACC, FUSED>(d, p, st);
+    case 32: return launch_bwd<VT, AT, 32, ACC, FUSED>(d, p, st);
+    case 64: return launch_bwd<VT, AT, 64, ACC, FUSED>(d, p, st);
   }
   return fail(MSDA_B200_ERR_UNSUPPORTED, "head dim %d", d->D);
 }
 
-}  // namespace
-
-extern "C" {
-
-int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
-
-const char* msda_b200_last_error(void) { return g_err; }
-
-int msda_b200_forward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn, void* out,
-                      const int32_t* query_order, void* stream) {
-  g_err[0] = 0;
-  if (int rc = validate(desc)) return rc;
-  if ((long long)desc->B * desc->Q == 0) return MSDA_B200_OK;
-  if (!value || !loc || !attn || !out) return fail(MSDA_B200_ERR_INVALID, "forward: NULL tensor pointer");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  KParams p;
-  memset(&p, 0, sizeof(p));
-  p.value = value; p.loc = loc; p.attn = attn; p.out = out; p.q_order = query_order;
+template <bool FUSED>
+int run_forward(const msda_b200_desc* desc, const KParams& p, cudaStream_t st) {
   const bool vbf = desc->value_dtype == MSDA_B200_BF16, abf = desc->attn_dtype == MSDA_B200_BF16;
-  if (!vbf) return dispatch_fwd<float, float>(desc, p, st);
-  if (abf) return dispatch_fwd<__nv_bfloat16, __nv_bfloat16>(desc, p, st);
-  return dispatch_fwd<__nv_bfloat16, float>(desc, p, st);
+  if (!vbf) return dispatch_fwd<float, float, FUSED>(desc, p, st);
+  if (abf) return dispatch_fwd<__nv_bfloat16, __nv_bfloat16, FUSED>(desc, p, st);
+  return dispatch_fwd<__nv_bfloat16, float, FUSED>(desc, p, st);
 }
 
-size_t msda_b200_backward_workspace_bytes(const msda_b200_desc* desc) {
-  if (!desc) return 0;
-  if (desc->value_dtype == MSDA_B200_BF16 && !(desc->flags & MSDA_B200_FLAG_BF16_ATOMICS))
-    return (size_t)desc->B * desc->S * desc->H * desc->D * sizeof(float);
-  return 0;
-}
-
-int msda_b200_backward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn,
-                       const void* grad_out, void* grad_value, float* grad_loc, void* grad_attn, void* workspace,
-                       size_t workspace_bytes, const int32_t* query_order, void* stream) {
-  g_err[0] = 0;
-  if (int rc = validate(desc)) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+// Shared by the plain and the fused backward: zero-fill, main kernel, bf16 conversion.
+template <bool FUSED>
+int run_backward(const msda_b200_desc* desc, KParams p, void* grad_value, void* workspace, size_t workspace_bytes,
+                 bool have_tensors, cudaStream_t st) {
   const bool prof = (desc->flags & MSDA_B200_FLAG_PROFILE) != 0;
   const bool vbf = desc->value_dtype == MSDA_B200_BF16, abf = desc->attn_dtype == MSDA_B200_BF16;
   const bool bf16_atomics = vbf && (desc->flags & MSDA_B200_FLAG_BF16_ATOMICS);
@@ -649,18 +727,14 @@ int msda_b200_backward(const msda_b200_desc* desc, const void* value, const floa
     if (cudaMemsetAsync(acc, 0, acc_bytes, st) != cudaSuccess) return check_launch("backward: memset");
   }
   if ((long long)desc->B * desc->Q != 0) {
-    if (!value || !loc || !attn || !grad_out || !grad_loc || !grad_attn)
-      return fail(MSDA_B200_ERR_INVALID, "backward: NULL tensor pointer");
-    KParams p;
-    memset(&p, 0, sizeof(p));
-    p.value = value; p.loc = loc; p.attn = attn; p.grad_out = grad_out; p.grad_value_acc = acc;
-    p.grad_loc = grad_loc; p.grad_attn = grad_attn; p.q_order = query_order;
+    if (!have_tensors) return fail(MSDA_B200_ERR_INVALID, "backward: NULL tensor pointer");
+    p.grad_value_acc = acc;
     int rc;
-    if (!vbf) rc = dispatch_bwd<float, float, 0>(desc, p, st);
-    else if (bf16_atomics) rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 1>(desc, p, st)
-                                    : dispatch_bwd<__nv_bfloat16, float, 1>(desc, p, st);
-    else rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 0>(desc, p, st)
-                  : dispatch_bwd<__nv_bfloat16, float, 0>(desc, p, st);
+    if (!vbf) rc = dispatch_bwd<float, float, 0, FUSED>(desc, p, st);
+    else if (bf16_atomics) rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 1, FUSED>(desc, p, st)
+                                    : dispatch_bwd<__nv_bfloat16, float, 1, FUSED>(desc, p, st);
+    else rc = abf ? dispatch_bwd<__nv_bfloat16, __nv_bfloat16, 0, FUSED>(desc, p, st)
+                  : dispatch_bwd<__nv_bfloat16, float, 0, FUSED>(desc, p, st);
     if (rc) return rc;
   }
   if (need && nvalue) {
@@ -673,6 +747,75 @@ int msda_b200_backward(const msda_b200_desc* desc, const void* value, const floa
     if (int rc = check_launch("backward: convert")) return rc;
   }
   return MSDA_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char* msda_b200_last_error(void) { return g_err; }
+
+int msda_b200_forward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn, void* out,
+                      const int32_t* query_order, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  if ((long long)desc->B * desc->Q == 0) return MSDA_B200_OK;
+  if (!value || !loc || !attn || !out) return fail(MSDA_B200_ERR_INVALID, "forward: NULL tensor pointer");
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.loc = loc; p.attn = attn; p.out = out; p.q_order = query_order;
+  return run_forward<false>(desc, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int msda_b200_forward_fused(const msda_b200_desc* desc, const void* value, const void* offsets, const void* logits,
+                            const float* ref_points, void* out, float* attn_out, const int32_t* query_order,
+                            void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  if ((long long)desc->B * desc->Q == 0) return MSDA_B200_OK;
+  if (!value || !offsets || !logits || !ref_points || !out)
+    return fail(MSDA_B200_ERR_INVALID, "forward_fused: NULL tensor pointer");
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.offsets = offsets; p.logits = logits; p.ref = ref_points; p.out = out; p.attn_out = attn_out;
+  p.q_order = query_order;
+  return run_forward<true>(desc, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t msda_b200_backward_workspace_bytes(const msda_b200_desc* desc) {
+  if (!desc) return 0;
+  if (desc->value_dtype == MSDA_B200_BF16 && !(desc->flags & MSDA_B200_FLAG_BF16_ATOMICS))
+    return (size_t)desc->B * desc->S * desc->H * desc->D * sizeof(float);
+  return 0;
+}
+
+int msda_b200_backward(const msda_b200_desc* desc, const void* value, const float* loc, const void* attn,
+                       const void* grad_out, void* grad_value, float* grad_loc, void* grad_attn, void* workspace,
+                       size_t workspace_bytes, const int32_t* query_order, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.loc = loc; p.attn = attn; p.grad_out = grad_out;
+  p.grad_loc = grad_loc; p.grad_attn = grad_attn; p.q_order = query_order;
+  const bool have = value && loc && attn && grad_out && grad_loc && grad_attn;
+  return run_backward<false>(desc, p, grad_value, workspace, workspace_bytes, have, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value, const void* offsets, const void* logits,
+                             const float* ref_points, const void* grad_out, void* grad_value, void* grad_offsets,
+                             void* grad_logits, void* workspace, size_t workspace_bytes, const int32_t* query_order,
+                             void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate(desc)) return rc;
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.value = value; p.offsets = offsets; p.logits = logits; p.ref = ref_points; p.grad_out = grad_out;
+  p.grad_offsets = grad_offsets; p.grad_logits = grad_logits; p.q_order = query_order;
+  const bool have = value && offsets && logits && ref_points && grad_out && grad_offsets && grad_logits;
+  return run_backward<true>(desc, p, grad_value, workspace, workspace_bytes, have, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int msda_b200_profile_ms(int which, float* ms) {

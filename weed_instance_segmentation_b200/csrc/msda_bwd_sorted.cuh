@@ -30,7 +30,7 @@ template <> struct Log2P<8> { static constexpr int v = 3; };
 
 struct SortedSmem {
   // byte offsets into dynamic shared memory
-  size_t w, ent, dot, a, xy, gc, go, cnt, fb, misc, total;
+  size_t w, ent, dot, a, xy, go, cnt, fb, misc, stat, total;
 };
 
 template <int NT, int TQ, int P, int CAP, int LPP>
@@ -43,12 +43,12 @@ __host__ __device__ inline SortedSmem sorted_smem_layout() {
   s.ent = o;  o += sizeof(int2) * NC;
   s.dot = o;  o += sizeof(float) * NC;
   s.a = o;    o += sizeof(float) * NS;
-  s.xy = o;   o += sizeof(int) * NS;
-  s.gc = o;   o += sizeof(int) * NS;
+  s.xy = o;   o += sizeof(int) * NS;  // x | y << 12 | derivative codes << 24 (level extents <= 4095)
   s.cnt = o;  o += sizeof(int) * (CAP + 4);
   s.fb = s.ent + sizeof(int2) * NC;  // fallback ids grow downwards from the end of the entry array (E + nfb <= NC)
   o = (o + 15) & ~size_t(15);
   s.misc = o; o += sizeof(int) * 64;
+  s.stat = o; o += sizeof(float) * 3 * TQ;  // fused prologue: softmax max, 1/sum, sum_k a_k*ga_k per query
   s.total = o;
   return s;
 }
@@ -58,8 +58,8 @@ enum { MI_MINX = 0, MI_MAXX, MI_MINY, MI_MAXY, MI_SUMX, MI_SUMY, MI_NACT, MI_FBN
 
 __device__ __forceinline__ float gdec(int code, int k) { return (float)(((code >> (2 * k)) & 3) - 1); }
 
-template <typename VT, typename AT, int D, int NT, int TQ, int P, int CAP, int ACC>
-__global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_constant__ KParams p) {
+template <typename VT, typename AT, int D, int NT, int TQ, int P, int CAP, int ACC, bool FUSED>
+__global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
   constexpr int G = NT / LPP;
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
   constexpr int WMAX = 256;  // window edge limit (8 bits per coordinate in the sort key)
   static_assert(CAP % NT == 0 && (CAP / NT) % 4 == 0, "scan assumes CAP/NT is a multiple of 4");
   static_assert(NC <= 65536, "entry ids are 16 bit");
+  static_assert(NS % NT == 0, "every thread owns NS/NT samples per level");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SortedSmem lay = sorted_smem_layout<NT, TQ, P, CAP, LPP>();
   float4* s_w = reinterpret_cast<float4*>(smem_raw + lay.w);
@@ -76,10 +77,12 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
   float* s_dot = reinterpret_cast<float*>(smem_raw + lay.dot);
   float* s_a = reinterpret_cast<float*>(smem_raw + lay.a);
   int* s_xy = reinterpret_cast<int*>(smem_raw + lay.xy);
-  int* s_gc = reinterpret_cast<int*>(smem_raw + lay.gc);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + lay.cnt);
   unsigned short* s_fb_end = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
   int* s_misc = reinterpret_cast<int*>(smem_raw + lay.misc);
+  float* s_max = reinterpret_cast<float*>(smem_raw + lay.stat);
+  float* s_inv = s_max + TQ;
+  float* s_dsum = s_inv + TQ;
 
   int b, tile, h;
   decode_block(p, b, tile, h);
@@ -116,12 +119,28 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
       if (l < p.L && si < NS && ql < nq) {
         const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
         const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
-        pre_loc[r] = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
-        pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[gi]);
+        if (FUSED) {
+          pre_loc[r] = fused_loc<AT>(p, gi, ((long long)b * p.Q + q) * p.L + l, p.lv[l]);
+          pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]);  // raw logit; softmax applied at use
+        } else {
+          pre_loc[r] = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
+          pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[gi]);
+        }
       }
     }
   };
   fetch_level(0);
+  if (FUSED) {
+    // softmax statistics of every (query, head) row of the tile; visible after the first barrier of the level loop
+    for (int ql = tid; ql < TQ; ql += NT) {
+      float mx = 0.f, inv = 0.f;
+      if (ql < nq) {
+        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+        softmax_stats<AT>(reinterpret_cast<const AT*>(p.logits) + (((long long)b * p.Q + q) * p.H + h) * p.LP, p.LP, mx, inv);
+      }
+      s_max[ql] = mx; s_inv[ql] = inv; s_dsum[ql] = 0.f;
+    }
+  }
 
   for (int l = 0; l < p.L; ++l) {
     const Level lv = p.lv[l];
@@ -141,12 +160,12 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
       const int si = r * NT + tid;
       const int ql = si >> LP2;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      int gcode = 0x55, xy = 0;  // code 1 == derivative 0
+      int gcode = 0x55;  // code 1 == derivative 0
       float a = 0.f;
       bool active = false;
       int xb = 0, yb = 0;
       if (si < NS && ql < nq) {
-        a = pre_a[r];
+        a = FUSED ? expf(pre_a[r] - s_max[ql]) * s_inv[ql] : pre_a[r];
         const Axis ax = axis_setup(pre_loc[r].x, lv.W), ay = axis_setup(pre_loc[r].y, lv.H);
         if (ax.ok && ay.ok) {
           w = make_float4(ax.s0, ax.s1, ay.s0, ay.s1);
@@ -156,10 +175,9 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
           active = xa && ya;
         }
         xb = ax.base; yb = ay.base;
-        xy = xb | (yb << 16);
       }
       if (si < NS) {
-        s_w[si] = w; s_a[si] = a; s_xy[si] = xy; s_gc[si] = gcode;
+        s_w[si] = w; s_a[si] = a; s_xy[si] = xb | (yb << 12) | (gcode << 24);
       }
       const unsigned act = __ballot_sync(0xffffffffu, active);
       if (act) {
@@ -203,12 +221,12 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     for (int id = tid; id < NC; id += NT) {
       const int si = id >> 2, cn = id & 3;
       const float4 w = s_w[si];
-      const int gcode = s_gc[si];
+      const int xy = s_xy[si];
+      const int gcode = xy >> 24;
       const bool xa = ((cn & 1) ? w.y : w.x) != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
       const bool ya = ((cn & 2) ? w.w : w.z) != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
       if (xa && ya) {
-        const int xy = s_xy[si];
-        const int px = (xy & 0xffff) + ((cn & 1) ? dxs : 0) - x0, py = (xy >> 16) + ((cn & 2) ? dys : 0) - y0;
+        const int px = (xy & 0xfff) + ((cn & 1) ? dxs : 0) - x0, py = ((xy >> 12) & 0xfff) + ((cn & 2) ? dys : 0) - y0;
         if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
           atomicAdd(&s_cnt[py * ww + px], 1);
         } else {
@@ -268,13 +286,13 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     for (int id = tid; id < NC; id += NT) {
       const int si = id >> 2, cn = id & 3;
       const float4 w = s_w[si];
-      const int gcode = s_gc[si];
+      const int xy = s_xy[si];
+      const int gcode = xy >> 24;
       const float wx = (cn & 1) ? w.y : w.x, wy = (cn & 2) ? w.w : w.z;
       const bool xa = wx != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
       const bool ya = wy != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
       if (xa && ya) {
-        const int xy = s_xy[si];
-        const int px = (xy & 0xffff) + ((cn & 1) ? dxs : 0) - x0, py = (xy >> 16) + ((cn & 2) ? dys : 0) - y0;
+        const int px = (xy & 0xfff) + ((cn & 1) ? dxs : 0) - x0, py = ((xy >> 12) & 0xfff) + ((cn & 2) ? dys : 0) - y0;
         if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
           const int slot = atomicAdd(&s_cnt[py * ww + px], 1);
           s_ent[slot] = make_int2((py << 24) | (px << 16) | id, __float_as_int(s_a[si] * wy * wx));
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
         const float4 w = s_w[si];
         const float wgt = s_a[si] * ((cn & 2) ? w.w : w.z) * ((cn & 1) ? w.y : w.x);
         const int xy = s_xy[si];
-        const int x = (xy & 0xffff) + ((cn & 1) ? dxs : 0), y = (xy >> 16) + ((cn & 2) ? dys : 0);
+        const int x = (xy & 0xfff) + ((cn & 1) ? dxs : 0), y = ((xy >> 12) & 0xfff) + ((cn & 2) ? dys : 0);
         const long long off = (long long)((lv.start + y * lv.W + x) * p.H + h) * LPP;
         float vf[VEC], gf[VEC];
         Vec16<VT>::unpack(ldg16(vb + off), vf);
@@ -385,20 +403,46 @@ __global__ void __launch_bounds__(NT) msda_bwd_sorted_kernel(const __grid_consta
     // ---- h: per-sample gradients
     for (int si = tid; si < NS; si += NT) {
       const int ql = si >> LP2, pt = si & (P - 1);
-      if (ql >= nq) continue;
-      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const bool valid = ql < nq;
+      const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
       const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
       const float4 d = *reinterpret_cast<const float4*>(&s_dot[si * 4]);
       const float4 w = s_w[si];
-      const int gcode = s_gc[si];
+      const int gcode = s_xy[si] >> 24;
       const float a = s_a[si];
       const float gl = gdec(gcode, 0), gr = gdec(gcode, 1), gt = gdec(gcode, 2), gb = gdec(gcode, 3);
       const float top_s = w.x * d.x + w.y * d.y, bot_s = w.x * d.z + w.y * d.w;
       const float top_g = gl * d.x + gr * d.y, bot_g = gl * d.z + gr * d.w;
-      reinterpret_cast<AT*>(p.grad_attn)[gi] = from_float<AT>(w.z * top_s + w.w * bot_s);
-      reinterpret_cast<float2*>(p.grad_loc)[gi] =
-          make_float2((float)lv.W * a * (w.z * top_g + w.w * bot_g), (float)lv.H * a * (gt * top_s + gb * bot_s));
+      const float g_attn = w.z * top_s + w.w * bot_s;
+      const float g_px = w.z * top_g + w.w * bot_g, g_py = gt * top_s + gb * bot_s;
+      if (!FUSED) {
+        if (valid) {
+          reinterpret_cast<AT*>(p.grad_attn)[gi] = from_float<AT>(g_attn);
+          reinterpret_cast<float2*>(p.grad_loc)[gi] = make_float2((float)lv.W * a * g_px, (float)lv.H * a * g_py);
+        }
+      } else {
+        if (valid) {
+          store_pair<AT>(p.grad_offsets, gi, a * g_px, a * g_py);
+          reinterpret_cast<AT*>(p.grad_logits)[gi] = from_float<AT>(g_attn);  // parked; finished after the last level
+        }
+        float t = valid ? a * g_attn : 0.f;  // the P samples of one (query, level) sit in P adjacent lanes
+#pragma unroll
+        for (int o = 1; o < P; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (valid && pt == 0) s_dsum[ql] += t;  // one writer per query and level; levels are separated by barriers
+      }
     }
     __syncthreads();
+  }
+
+  if (FUSED) {
+    // softmax backward over the L*P logits of each (query, head): g_j = a_j * (ga_j - sum_k a_k ga_k)
+    for (int i = tid; i < nq * p.LP; i += NT) {
+      const int ql = i / p.LP, sidx = i - ql * p.LP;
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + sidx;
+      const float a = expf(to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]) - s_max[ql]) * s_inv[ql];
+      const float ga = to_float<AT>(reinterpret_cast<const AT*>(p.grad_logits)[gi]);
+      reinterpret_cast<AT*>(p.grad_logits)[gi] = from_float<AT>(a * (ga - s_dsum[ql]));
+    }
   }
 }
