@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 1
+#define MSDA_B200_ABI_VERSION 2
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -112,6 +112,27 @@ int msda_b200_backward(const msda_b200_desc* desc, const void* value /*dev*/, co
                        const void* attn /*dev*/, const void* grad_out /*dev*/, void* grad_value /*dev*/,
                        float* grad_loc /*dev*/, void* grad_attn /*dev*/, void* workspace /*dev|NULL*/,
                        size_t workspace_bytes, const int32_t* query_order /*dev|NULL*/, void* stream);
+
+/*
+ * Fused-prologue variants.  Replace M2F:952-971 + M2F:798-837 in one launch: the kernel takes the raw outputs
+ * of the module's `sampling_offsets` and `attention_weights` projections and computes
+ *   attn = softmax(logits over the L*P entries of each (query, head))                 (M2F:955-960)
+ *   loc  = ref_points[b,q,l,:] + offsets[b,q,h,l,p,:] / (W_l, H_l)                     (M2F:962-971)
+ * on the fly, so sampling_locations and attention_weights never round-trip through HBM.
+ *   offsets (B,Q,H,L,P,2) and logits (B,Q,H,L*P): dtype = attn_dtype;  ref_points (B,Q,L,2) float32.
+ *   attn_out (optional, float32, (B,Q,H,L,P)): the softmax output, for callers that return it (M2F:983).
+ * The backward writes grad_offsets / grad_logits (dtype = attn_dtype); reference points get no gradient
+ * (they are constants of the geometry, M2F:1095-1125).
+ */
+int msda_b200_forward_fused(const msda_b200_desc* desc, const void* value /*dev*/, const void* offsets /*dev*/,
+                            const void* logits /*dev*/, const float* ref_points /*dev*/, void* out /*dev*/,
+                            float* attn_out /*dev|NULL*/, const int32_t* query_order /*dev|NULL*/, void* stream);
+
+int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value /*dev*/, const void* offsets /*dev*/,
+                             const void* logits /*dev*/, const float* ref_points /*dev*/, const void* grad_out /*dev*/,
+                             void* grad_value /*dev*/, void* grad_offsets /*dev*/, void* grad_logits /*dev*/,
+                             void* workspace /*dev|NULL*/, size_t workspace_bytes,
+                             const int32_t* query_order /*dev|NULL*/, void* stream);
 
 /*
  * Profiling aid for bench.py: when desc->flags has MSDA_B200_FLAG_PROFILE the library records

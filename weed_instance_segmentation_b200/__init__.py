@@ -11,12 +11,14 @@ from .functional import (  # noqa: F401
     multi_scale_deformable_attention,
     query_order_2d,
 )
+from .fused import MSDeformAttnFusedFunction, ms_deform_attn_fused  # noqa: F401
 from .hf_patch import install, installed, is_installed, uninstall  # noqa: F401
 
 __all__ = [
     "MSDAError",
     "MSDeformAttnFunction",
     "ms_deform_attn",
+    "ms_deform_attn_fused",
     "multi_scale_deformable_attention",
     "query_order_2d",
     "install",

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .functional import ms_deform_attn
+from .fused import ms_deform_attn_fused
 
 
 class MSDeformAttn(nn.Module):
@@ -44,6 +45,8 @@ class MSDeformAttn(nn.Module):
         # Mask2FormerPixelDecoder.forward always passes all-False padding masks (M2F:1307-1309), which
         # makes masked_fill (M2F:948-950) a full-tensor no-op; convert_pixel_decoder() sets this to skip it.
         self.assume_no_padding = False
+        # Compute softmax and sampling locations inside the kernels (fused.py); convert_pixel_decoder() enables it.
+        self.fused_prologue = False
 
     @classmethod
     def from_hf(cls, mod: nn.Module) -> "MSDeformAttn":
@@ -57,6 +60,7 @@ class MSDeformAttn(nn.Module):
         new.value_proj = mod.value_proj
         new.output_proj = mod.output_proj
         new.assume_no_padding = False
+        new.fused_prologue = False
         new.train(mod.training)
         return new
 
@@ -93,6 +97,13 @@ class MSDeformAttn(nn.Module):
         value = value.view(batch_size, sequence_length, H, self.d_model // H)
         sampling_offsets = self.sampling_offsets(hidden_states).view(batch_size, num_queries, H, L, P, 2)
         attention_weights = self.attention_weights(hidden_states).view(batch_size, num_queries, H, L * P)
+        if self.fused_prologue and reference_points.shape[-1] == 2 and not reference_points.requires_grad:
+            # softmax (M2F:955-960) and ref + off / (W, H) (M2F:962-971) happen inside the kernels
+            res = ms_deform_attn_fused(value, spatial_shapes_list, level_start_index, sampling_offsets,
+                                       attention_weights, reference_points,
+                                       return_attention_weights=output_attentions)
+            output, attention_weights = res if output_attentions else (res, None)
+            return self.output_proj(output), attention_weights
         attention_weights = F.softmax(attention_weights, -1).view(batch_size, num_queries, H, L, P)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.tensor(
@@ -194,7 +205,7 @@ class EncoderLayer(nn.Module):
         return outputs
 
 
-def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True) -> int:
+def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fused_prologue: bool = True) -> int:
     """Replace every HF pixel-decoder encoder layer (and its MSDeformAttn) inside ``model`` by the
     mirrors above, sharing parameters. Returns the number of layers converted.
 
@@ -211,6 +222,7 @@ def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True) -> i
                     continue
                 new = EncoderLayer.from_hf(layer)
                 new.self_attn.assume_no_padding = assume_no_padding
+                new.self_attn.fused_prologue = fused_prologue
                 module.layers[i] = new
                 converted += 1
     return converted
