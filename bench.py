@@ -199,14 +199,17 @@ def workload_config(dist, dtype):
 class Problem:
     """Device buffers + descriptor for direct C-ABI calls (no autograd in the timed region)."""
 
-    def __init__(self, dist, dtype, device, seed):
+    def __init__(self, dist, dtype, device, seed, shapes=None, batch=None):
         import torch
         from weed_instance_segmentation_b200 import _cabi, functional
         from weed_instance_segmentation_b200.synth import msda_inputs
         self.torch, self.cabi = torch, _cabi
         self.lib = _cabi.load()
         tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
-        x = msda_inputs(B_PER_GPU, SHAPES_C2, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=seed,
+        shapes = SHAPES_C2 if shapes is None else shapes
+        batch = B_PER_GPU if batch is None else batch
+        self.shapes, self.batch = shapes, batch
+        x = msda_inputs(batch, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=seed,
                         device=device, value_dtype=tdt)
         self.x = x
         self.value, self.loc, self.attn, self.go = (x["value"], x["sampling_locations"], x["attention_weights"],
@@ -216,14 +219,14 @@ class Problem:
         self.gv, self.gl, self.ga = torch.empty_like(self.value), torch.empty_like(self.loc), torch.empty_like(self.attn)
         code = _cabi.BF16 if dtype == "bf16" else _cabi.F32
         lsi = x["level_start_index"].tolist()
-        self.order = functional.query_order_2d(SHAPES_C2, functional._TILE, device) if functional._USE_ORDER else None
+        self.order = functional.query_order_2d(shapes, functional._TILE, device) if functional._USE_ORDER else None
         self.flags = _cabi.FLAG_BF16_ATOMICS if (functional._BF16_ATOMICS and dtype == "bf16") else 0
         if functional._BWD_V1:
             self.flags |= _cabi.FLAG_BWD_V1
         if functional._BWD_TQ256:
             self.flags |= _cabi.FLAG_BWD_TQ256
-        self.desc, self._keep = _cabi.make_desc(B_PER_GPU, self.S, self.S, H, D, L, P, code, code, SHAPES_C2, lsi, self.flags)
-        self.pdesc, self._keep2 = _cabi.make_desc(B_PER_GPU, self.S, self.S, H, D, L, P, code, code, SHAPES_C2, lsi,
+        self.desc, self._keep = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi, self.flags)
+        self.pdesc, self._keep2 = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi,
                                                   self.flags | _cabi.FLAG_PROFILE)
         nws = int(self.lib.msda_b200_backward_workspace_bytes(self.desc))
         self.ws = torch.empty(nws, dtype=torch.uint8, device=device) if nws else None
@@ -385,6 +388,24 @@ def run_b200(args, rank, world, local_rank):
                                        "frac_of_hbm_peak": (f2 + b2) / s2 / 1e9 / peak}
             del p2
             torch.cuda.empty_cache()
+        # the other BASELINE.json geometries the op sees (per layer): config 3 (966x1296, batch 16) fwd+bwd and
+        # config 5 (2048x2048 inference, batch 4) forward only
+        from weed_instance_segmentation_b200.synth import pixel_decoder_shapes
+        n = max(10, args.steps // 4)
+        p3 = Problem("init", "bf16", device, seed=rank, shapes=pixel_decoder_shapes(966, 1296), batch=16)
+        s3 = time_steps(torch, p3.step, n, 3, barrier) / n
+        extras["config3 966x1296 B=16 bf16 fwd+bwd"] = {
+            "ms_per_step": s3 * 1e3, "images_per_s": 16 / s3,
+            "frac_of_hbm_peak": sum(algorithmic_bytes(16, p3.S, "bf16")) / s3 / 1e9 / peak}
+        del p3
+        torch.cuda.empty_cache()
+        p5 = Problem("init", "bf16", device, seed=rank, shapes=pixel_decoder_shapes(2048, 2048), batch=4)
+        s5 = time_steps(torch, p5.fwd, n, 3, barrier) / n
+        extras["config5 2048x2048 B=4 bf16 fwd only"] = {
+            "ms_per_step": s5 * 1e3, "images_per_s": 4 / s5,
+            "frac_of_hbm_peak": algorithmic_bytes(4, p5.S, "bf16")[0] / s5 / 1e9 / peak}
+        del p5
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
