@@ -307,48 +307,45 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
       const int E = s_misc[MI_TOTAL];
       const int per = (E + G - 1) / G;
       const int e0 = g * per;
+      const int e_end = min(e0 + per, E);
+      // window pixel (px, py) -> 16-byte-unit offset inside the batch item: base0 + py * sy + px * sx
+      const int sx = p.H * LPP, sy = lv.W * sx;
+      const int base0 = ((lv.start + y0 * lv.W + x0) * p.H + h) * LPP;
+      char* const acc_ptr = reinterpret_cast<char*>(p.grad_value_acc) +
+                            (acc_base + c) * (long long)(VEC * (ACC == 0 ? sizeof(float) : sizeof(VT)));
+      const uint4* const go_lane = s_go + c;
       int cur = -1, cur_off = 0;
       float acc[VEC], vf[VEC];
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; vf[j] = 0.f; }
       auto flush = [&]() {
         if (ACC == 0) {
-          float* dst = reinterpret_cast<float*>(p.grad_value_acc) + (acc_base + c) * VEC + (long long)cur_off * VEC;
+          float* dst = reinterpret_cast<float*>(acc_ptr + (long long)cur_off * (VEC * (int)sizeof(float)));
 #pragma unroll
           for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         } else {
           const uint4 pk = Vec16<VT>::pack(acc);
-          red_add_bf16x8(reinterpret_cast<VT*>(p.grad_value_acc) + (acc_base + c) * VEC + (long long)cur_off * VEC,
-                         pk.x, pk.y, pk.z, pk.w);
+          red_add_bf16x8(acc_ptr + (long long)cur_off * (VEC * (int)sizeof(VT)), pk.x, pk.y, pk.z, pk.w);
         }
       };
-      // software pipeline: entry k+2 and the grad_out row of entry k+1 are in flight while entry k is processed
-      constexpr int PAD = (int)0xffff0000u;  // padding entry (beyond the share or the list): weight 0, dot discarded
-      const int e_end = min(e0 + per, E);
-      auto load_entry = [&](int e) { return e < e_end ? s_ent[e] : make_int2(PAD, 0); };
-      auto go_row = [&](const int2& en) { return s_go[((en.x & 0xffff) >> (2 + LP2)) * LPP + c]; };
-      int2 en_next = load_entry(e0), en_next2 = load_entry(e0 + 1);
-      uint4 go_next = go_row(en_next);
       for (int k = 0; k < per; ++k) {
-        const int2 en = en_next;
-        const uint4 go_raw = go_next;
-        en_next = en_next2;
-        en_next2 = load_entry(e0 + k + 2);
-        go_next = go_row(en_next);
-        const bool valid = en.x != PAD;
+        const int e = e0 + k;
+        const bool valid = e < e_end;
+        int2 en = make_int2(cur << 16, 0);  // padding: same pixel, weight 0, dot discarded
+        if (valid) en = s_ent[e];
         const int pix = (int)((unsigned)en.x >> 16);
         const int id = en.x & 0xffff;
         const float wgt = __int_as_float(en.y);
         if (valid && pix != cur) {
           if (cur >= 0) flush();
           cur = pix;
-          cur_off = ((lv.start + (y0 + (pix >> 8)) * lv.W + (x0 + (pix & 0xff))) * p.H + h) * LPP;
+          cur_off = base0 + (pix >> 8) * sy + (pix & 0xff) * sx;
           Vec16<VT>::unpack(ldg16(vb + cur_off), vf);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
         }
         float gf[VEC];
-        Vec16<VT>::unpack(go_raw, gf);
+        Vec16<VT>::unpack(go_lane[(id >> (2 + LP2)) * LPP], gf);
         float d = 0.f;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
