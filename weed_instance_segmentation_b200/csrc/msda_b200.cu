@@ -659,13 +659,13 @@ bool sorted_applicable(const msda_b200_desc* d) {
   return true;
 }
 
-template <typename VT, typename AT, int ACC, bool FUSED, int kNT, int kTQ>
+template <typename VT, typename AT, int ACC, bool FUSED, int kNT, int kTQ, int kPL>
 int launch_bwd_sorted_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int D = 32, P = 4;
   constexpr int LPP = D / Vec16<VT>::N;
   fill_geometry(d, p, kTQ);
   const size_t smem = sorted_smem_layout<kNT, kTQ, P, kSortCAP, LPP>().total;
-  auto kern = msda_bwd_sorted_kernel<VT, AT, D, kNT, kTQ, P, kSortCAP, ACC, FUSED>;
+  auto kern = msda_bwd_sorted_kernel<VT, AT, D, kNT, kTQ, P, kSortCAP, ACC, FUSED, kPL>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
   const long long blocks = (long long)p.B * p.num_tiles * p.H;
@@ -682,8 +682,8 @@ template <typename VT, typename AT, int ACC, bool FUSED>
 int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
   if constexpr (std::is_same<VT, __nv_bfloat16>::value) {
     if (sorted_applicable(d)) {
-      if (d->flags & MSDA_B200_FLAG_BWD_TQ256) return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, 512, 256>(d, p, st);
-      return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, kSortNT, kSortTQ>(d, p, st);
+      if (d->flags & MSDA_B200_FLAG_BWD_TQ256) return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, kSortNT, kSortTQ, 2>(d, p, st);
+      return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, kSortNT, kSortTQ, 4>(d, p, st);
     }
   }
   switch (d->D) {

@@ -58,7 +58,7 @@ enum { MI_MINX = 0, MI_MAXX, MI_MINY, MI_MAXY, MI_SUMX, MI_SUMY, MI_NACT, MI_FBN
 
 __device__ __forceinline__ float gdec(int code, int k) { return (float)(((code >> (2 * k)) & 3) - 1); }
 
-template <typename VT, typename AT, int D, int NT, int TQ, int P, int CAP, int ACC, bool FUSED>
+template <typename VT, typename AT, int D, int NT, int TQ, int P, int CAP, int ACC, bool FUSED, int PULL_LANES>
 __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -301,31 +301,46 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
     }
     __syncthreads();
 
-    // ---- f: pull over the sorted list: every lane group walks `per` consecutive entries (the same trip
-    // count for all groups, so the warp stays convergent and the dot reduction can use full-mask shuffles)
+    // ---- f: pull over the sorted list: PL lanes share one entry (each lane owns CH 16-byte chunks of the
+    // row); every lane group walks `per` consecutive entries -- the same trip count for all groups, so the
+    // warp stays convergent and the dot reduction can use full-mask shuffles
     {
+      constexpr int PL = (LPP >= PULL_LANES) ? PULL_LANES : LPP;  // lanes per entry
+      constexpr int CH = LPP / PL;                               // 16-byte chunks per lane
+      constexpr int GP = NT / PL;                                // entries in flight per block
+      const int pg = tid / PL, pc = (tid % PL) * CH;
       const int E = s_misc[MI_TOTAL];
-      const int per = (E + G - 1) / G;
-      const int e0 = g * per;
+      // share length per lane group, forced odd: the groups of a warp then read their 8-byte entries from
+      // distinct banks (an even share -- 2048 entries / 64 groups = 32 is the common case -- puts all of them
+      // 256 B apart, an 8-way bank conflict on every entry load)
+      const int per = ((E + GP - 1) / GP) | 1;
+      const int e0 = pg * per;
       const int e_end = min(e0 + per, E);
       // window pixel (px, py) -> 16-byte-unit offset inside the batch item: base0 + py * sy + px * sx
       const int sx = p.H * LPP, sy = lv.W * sx;
-      const int base0 = ((lv.start + y0 * lv.W + x0) * p.H + h) * LPP;
-      char* const acc_ptr = reinterpret_cast<char*>(p.grad_value_acc) +
-                            (acc_base + c) * (long long)(VEC * (ACC == 0 ? sizeof(float) : sizeof(VT)));
-      const uint4* const go_lane = s_go + c;
+      const int base0 = ((lv.start + y0 * lv.W + x0) * p.H + h) * LPP + pc;
+      constexpr int kChunkBytes = VEC * (ACC == 0 ? (int)sizeof(float) : (int)sizeof(VT));
+      char* const acc_ptr = reinterpret_cast<char*>(p.grad_value_acc) + acc_base * (long long)kChunkBytes;
+      const uint4* const vrow = reinterpret_cast<const uint4*>(p.value) + acc_base;
+      const uint4* const go_lane = s_go + pc;
       int cur = -1, cur_off = 0;
-      float acc[VEC], vf[VEC];
+      float acc[CH][VEC], vf[CH][VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { acc[j] = 0.f; vf[j] = 0.f; }
+      for (int u = 0; u < CH; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { acc[u][j] = 0.f; vf[u][j] = 0.f; }
       auto flush = [&]() {
-        if (ACC == 0) {
-          float* dst = reinterpret_cast<float*>(acc_ptr + (long long)cur_off * (VEC * (int)sizeof(float)));
 #pragma unroll
-          for (int j = 0; j < VEC; j += 4) red_add_f32x4(dst + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        } else {
-          const uint4 pk = Vec16<VT>::pack(acc);
-          red_add_bf16x8(acc_ptr + (long long)cur_off * (VEC * (int)sizeof(VT)), pk.x, pk.y, pk.z, pk.w);
+        for (int u = 0; u < CH; ++u) {
+          char* dst = acc_ptr + (long long)(cur_off + u) * kChunkBytes;
+          if (ACC == 0) {
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4)
+              red_add_f32x4(reinterpret_cast<float*>(dst) + j, acc[u][j], acc[u][j + 1], acc[u][j + 2], acc[u][j + 3]);
+          } else {
+            const uint4 pk = Vec16<VT>::pack(acc[u]);
+            red_add_bf16x8(dst, pk.x, pk.y, pk.z, pk.w);
+          }
         }
       };
       for (int k = 0; k < per; ++k) {
@@ -340,21 +355,27 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
           if (cur >= 0) flush();
           cur = pix;
           cur_off = base0 + (pix >> 8) * sy + (pix & 0xff) * sx;
-          Vec16<VT>::unpack(ldg16(vb + cur_off), vf);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+          for (int u = 0; u < CH; ++u) {
+            Vec16<VT>::unpack(ldg16(vrow + cur_off + u), vf[u]);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) acc[u][j] = 0.f;
+          }
         }
-        float gf[VEC];
-        Vec16<VT>::unpack(go_lane[(id >> (2 + LP2)) * LPP], gf);
         float d = 0.f;
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          acc[j] = fmaf(wgt, gf[j], acc[j]);
-          d = fmaf(gf[j], vf[j], d);
+        for (int u = 0; u < CH; ++u) {
+          float gf[VEC];
+          Vec16<VT>::unpack(go_lane[(id >> (2 + LP2)) * LPP + u], gf);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            acc[u][j] = fmaf(wgt, gf[j], acc[u][j]);
+            d = fmaf(gf[j], vf[u][j], d);
+          }
         }
 #pragma unroll
-        for (int o = 1; o < LPP; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        if (valid && c == 0) s_dot[id] = d;
+        for (int o = 1; o < PL; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        if (valid && pc == 0) s_dot[id] = d;
       }
       if (cur >= 0) flush();
     }
