@@ -166,6 +166,38 @@ def throughput(trainer: Trainer, batches: list, steps: int, warmup: int) -> floa
     return secs
 
 
+def inference_throughput(model, device, args, rank: int) -> float:
+    """Seconds for ``args.steps`` forward passes on one replica (max over ranks when run under torchrun)."""
+    model = model.to(device).eval()
+    g = torch.Generator().manual_seed(rank)
+    pixel_values = torch.randn(args.batch, 3, args.height, args.width, generator=g).to(device)
+    amp = (torch.autocast(device.type, dtype=torch.bfloat16) if args.amp == "bf16" else contextlib.nullcontext())
+    multi = dist.is_available() and dist.is_initialized()
+
+    def step():
+        with torch.no_grad(), amp:
+            return model(pixel_values=pixel_values)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) / 1e3
+    if multi:
+        dist.barrier()
+        t = torch.tensor([secs], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    return secs
+
+
 def main(argv=None):
     import argparse
     import json
@@ -180,6 +212,9 @@ def main(argv=None):
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--impl", choices=["b200", "b200-function", "reference"], default="b200")
     ap.add_argument("--amp", choices=["none", "bf16"], default="none")
+    ap.add_argument("--infer", action="store_true",
+                    help="inference replicas instead of training (the reference's run_inference call shape, "
+                         "/root/reference/models/mask2former/inference.py:25-30): eval(), no_grad, no collective")
     args = ap.parse_args(argv)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,6 +231,20 @@ def main(argv=None):
         use_b200_path(model, "modules")
     elif args.impl == "b200-function":
         use_b200_path(model, "function")
+    if args.infer:
+        secs = inference_throughput(model, device, args, rank)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "mask2former_inference_throughput", "value": world * args.batch * args.steps / secs,
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": secs / args.steps * 1e3, "impl": args.impl, "scaling": "weak (independent replicas)",
+                "data": "synthetic", "dtype": "bf16 autocast" if args.amp == "bf16" else "f32",
+                "config": {"workload": f"Mask2Former {args.backbone} inference, {args.height}x{args.width}, "
+                                       f"batch {args.batch}/GPU"},
+            }), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     trainer = Trainer(model, device, amp_dtype=torch.bfloat16 if args.amp == "bf16" else None)
     batches = [synth.collate_batch(args.batch, args.height, args.width, num_classes=args.classes, seed=1000 * rank + i)
                for i in range(2)]
