@@ -7,6 +7,7 @@ Compares, with identical weights and inputs:
   function  : stock HF layer, op rebound to the B200 operator (hf_patch.install)
   modules   : modules.EncoderLayer + MSDeformAttn, un-fused prologue
   fused     : modules.EncoderLayer + MSDeformAttn with the fused softmax/location prologue
+  fused+norm: the same plus the fused residual + LayerNorm kernels (layer_norm.py)
 
     python bench_layer.py [--amp bf16|none] [--steps K] [--warmup W] [--batch B]
 Prints one JSON line.
@@ -61,10 +62,11 @@ def main():
 
     def variant(name):
         layer = copy.deepcopy(ref_layer)
-        if name in ("modules", "fused"):
+        if name in ("modules", "fused", "fused+norm"):
             layer = modules.EncoderLayer.from_hf(layer)
             layer.self_attn.assume_no_padding = True
-            layer.self_attn.fused_prologue = name == "fused"
+            layer.self_attn.fused_prologue = name != "modules"
+            layer.fused_norm = name == "fused+norm"
         return layer
 
     def run(layer, patched):
@@ -99,13 +101,13 @@ def main():
         return timed()
 
     results, outs = {}, {}
-    for name, patched in (("reference", False), ("function", True), ("modules", True), ("fused", True)):
+    for name, patched in (("reference", False), ("function", True), ("modules", True), ("fused", True), ("fused+norm", True)):
         ms, out, gx = run(variant(name), patched)
         results[name] = {"ms_per_layer_fwd_bwd": ms}
         outs[name] = (out, gx)
         torch.cuda.empty_cache()
     r_out, r_gx = outs["reference"]
-    for name in ("function", "modules", "fused"):
+    for name in ("function", "modules", "fused", "fused+norm"):
         o, g = outs[name]
         results[name]["out_rel_err_vs_reference"] = ((o - r_out).abs().max() / r_out.abs().max()).item()
         results[name]["grad_input_rel_err_vs_reference"] = ((g - r_gx).abs().max() / r_gx.abs().max()).item()

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 2
+#define MSDA_B200_ABI_VERSION 3
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -133,6 +133,26 @@ int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value /*dev
                              void* grad_value /*dev*/, void* grad_offsets /*dev*/, void* grad_logits /*dev*/,
                              void* workspace /*dev|NULL*/, size_t workspace_bytes,
                              const int32_t* query_order /*dev|NULL*/, void* stream);
+
+/*
+ * Encoder-layer epilogue: fused residual add + LayerNorm over rows of `channels`
+ * (a multiple of 128, at most 512; 256 in Mask2Former).  Replaces M2F:1049-1050 and M2F:1058-1059,
+ *   y = LayerNorm(x + residual) * gamma + beta,
+ * and their autograd nodes.  x / residual may be float32 or bfloat16 (dtype codes as above); y, mean, rstd,
+ * gamma, beta and every gradient are float32.  grad_sum is d loss / d (x + residual), i.e. the gradient of both
+ * inputs; grad_sum_lowp (optional) receives the same values in bfloat16 for a bfloat16 x.  The library zero-fills
+ * grad_gamma / grad_beta before accumulating.
+ */
+int msda_b200_add_layernorm_forward(const void* x /*dev*/, int x_dtype, const void* residual /*dev*/, int residual_dtype,
+                                    const float* gamma /*dev*/, const float* beta /*dev*/, float eps, float* y /*dev*/,
+                                    float* mean /*dev, rows*/, float* rstd /*dev, rows*/, int64_t rows, int32_t channels,
+                                    void* stream);
+
+int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* x /*dev*/, int x_dtype,
+                                     const void* residual /*dev*/, int residual_dtype, const float* gamma /*dev*/,
+                                     const float* mean /*dev*/, const float* rstd /*dev*/, float* grad_sum /*dev*/,
+                                     void* grad_sum_lowp /*dev|NULL*/, float* grad_gamma /*dev*/, float* grad_beta /*dev*/,
+                                     int64_t rows, int32_t channels, void* stream);
 
 /*
  * Profiling aid for bench.py: when desc->flags has MSDA_B200_FLAG_PROFILE the library records

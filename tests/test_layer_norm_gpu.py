@@ -1,0 +1,53 @@
+"""Fused residual-add + LayerNorm (csrc/layer_epilogue.cu) against torch's add + F.layer_norm (M2F:1049-1050)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("rows", [1, 7, 64, 1000, 21504])
+@pytest.mark.parametrize("C", [128, 256, 512])
+@pytest.mark.parametrize("xdt,rdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                     (torch.bfloat16, torch.bfloat16)])
+def test_add_layer_norm_matches_torch(rows, C, xdt, rdt):
+    from weed_instance_segmentation_b200.layer_norm import add_layer_norm
+    g = torch.Generator(device="cuda").manual_seed(rows * 7 + C)
+    x = torch.randn(2, rows, C, device="cuda", generator=g).to(xdt).requires_grad_(True)
+    r = (3.0 * torch.randn(2, rows, C, device="cuda", generator=g) + 0.5).to(rdt).requires_grad_(True)
+    w = (1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    go = torch.randn(2, rows, C, device="cuda", generator=g)
+    y = add_layer_norm(x, r, w, b, 1e-5)
+    assert y.dtype == torch.float32
+    y.backward(go)
+    got = [y.detach(), x.grad.clone(), r.grad.clone(), w.grad.clone(), b.grad.clone()]
+    # reference in fp64 on the same (rounded) inputs
+    xr, rr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, r, w, b))
+    yr = F.layer_norm(rr + xr, (C,), wr, br, 1e-5)
+    yr.backward(go.double())
+    want = [yr.detach(), xr.grad, rr.grad, wr.grad, br.grad]
+    bars = [1e-5, 1e-5 if xdt == torch.float32 else 1e-2, 1e-5 if rdt == torch.float32 else 1e-2, 2e-5, 2e-5]
+    for name, a, c, bar in zip(("y", "grad_x", "grad_r", "grad_w", "grad_b"), got, want, bars):
+        assert a.shape == c.shape
+        assert _rel(a, c) <= bar, (name, _rel(a, c))
+
+
+def test_add_layer_norm_errors():
+    from weed_instance_segmentation_b200 import MSDAError
+    from weed_instance_segmentation_b200.layer_norm import add_layer_norm
+    x = torch.zeros(4, 96, device="cuda")
+    with pytest.raises(MSDAError):  # 96 channels: not a multiple of 128
+        add_layer_norm(x, x, torch.ones(96, device="cuda"), torch.zeros(96, device="cuda"))
+    with pytest.raises(ValueError):
+        add_layer_norm(torch.zeros(4, 128, device="cuda"), torch.zeros(5, 128, device="cuda"),
+                       torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
+    with pytest.raises(RuntimeError):
+        add_layer_norm(torch.zeros(4, 128), torch.zeros(4, 128), torch.ones(128), torch.zeros(128))
+    y = add_layer_norm(torch.zeros(0, 128, device="cuda"), torch.zeros(0, 128, device="cuda"),
+                       torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
+    assert y.shape == (0, 128)

@@ -1,0 +1,31 @@
+"""Kernel-level time split of one fused-prologue encoder layer fwd+bwd under bf16 autocast (torch profiler)."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from transformers import Mask2FormerConfig
+from transformers.models.mask2former import modeling_mask2former as m2f
+import weed_instance_segmentation_b200 as wis
+from weed_instance_segmentation_b200 import modules, synth
+
+SHAPES = [(32, 32), (64, 64), (128, 128)]
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+layer = modules.EncoderLayer.from_hf(m2f.Mask2FormerPixelDecoderEncoderLayer(Mask2FormerConfig()).to(dev).train())
+layer.self_attn.assume_no_padding = True
+layer.self_attn.fused_prologue = True
+S = sum(h * w for h, w in SHAPES); B = 8
+x = torch.randn(B, S, 256, device=dev, requires_grad=True); pos = torch.randn(B, S, 256, device=dev)
+mask = torch.zeros(B, S, dtype=torch.bool, device=dev)
+ref = synth.reference_points(SHAPES, device=dev)[None].expand(B, -1, -1, -1).contiguous()
+lsi = torch.tensor(synth.level_start_index(SHAPES), device=dev); go = torch.randn(B, S, 256, device=dev)
+
+def step():
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = layer(x, mask, position_embeddings=pos, reference_points=ref, spatial_shapes_list=SHAPES, level_start_index=lsi)[0]
+    out.backward(go.to(out.dtype))
+
+for _ in range(3): step()
+torch.cuda.synchronize()
+with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+    for _ in range(5): step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))

@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 8
 F32, BF16 = 0, 1
 FLAG_PROFILE = 1
@@ -29,6 +29,8 @@ EXPORTS = (
     "msda_b200_backward",
     "msda_b200_forward_fused",
     "msda_b200_backward_fused",
+    "msda_b200_add_layernorm_forward",
+    "msda_b200_add_layernorm_backward",
     "msda_b200_profile_ms",
     "msda_b200_launch_count",
 )
@@ -84,6 +86,12 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_forward_fused.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.msda_b200_backward_fused.restype = ctypes.c_int
     lib.msda_b200_backward_fused.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]
+    lib.msda_b200_add_layernorm_forward.restype = ctypes.c_int
+    lib.msda_b200_add_layernorm_forward.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_float, vp, vp, vp,
+                                                    ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_add_layernorm_backward.restype = ctypes.c_int
+    lib.msda_b200_add_layernorm_backward.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,
+                                                     ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_profile_ms.restype = ctypes.c_int
     lib.msda_b200_profile_ms.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.msda_b200_launch_count.restype = ctypes.c_int64

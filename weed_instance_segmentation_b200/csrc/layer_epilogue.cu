@@ -1,0 +1,264 @@
+// layer_epilogue.cu -- fused residual-add + LayerNorm for the pixel-decoder encoder layer.
+//
+// Replaces, on both sides of the MSDeformAttn op,
+//     hidden_states = residual + hidden_states                      (M2F:1049, M2F:1058)
+//     hidden_states = self.{self_attn,final}_layer_norm(hidden_states)   (M2F:1050, M2F:1059)
+// and their autograd nodes by one kernel per direction. Rows are d_model wide (256 in Mask2Former); one warp owns
+// one row, statistics in fp32 registers, 16-byte accesses. Under autocast the branch input is bf16 (GEMM output)
+// and the residual fp32; the output is fp32, as torch's autocast LayerNorm produces.
+//
+//   forward : y = (s - mean(s)) * rstd(s) * gamma + beta,  s = x + r        (saves mean, rstd)
+//   backward: ds = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma,  xhat = (s - mean) * rstd
+//             dgamma = sum_rows dy * xhat,  dbeta = sum_rows dy             (block partials -> fp32 atomics)
+//             ds is the gradient of both x and r; it is written in fp32 and, if asked, also in x's dtype.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "msda_b200.h"
+
+extern "C" int msda_b200_internal_fail(int code, const char* msg);  // msda_b200.cu: sets msda_b200_last_error()
+
+namespace {
+
+constexpr int kMaxC = 512;             // up to 4 float4 chunks per lane (backward keeps 32 KB of block partials)
+constexpr int kRowsPerBlock = 8;       // 8 warps
+constexpr int kThreads = kRowsPerBlock * 32;
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const void* base, long long idx4);
+template <>
+__device__ __forceinline__ float4 load4<float>(const void* base, long long idx4) {
+  return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const void* base, long long idx4) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(base) + idx4);
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ void store4_bf16(void* base, long long idx4, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const unsigned*>(&lo);
+  o.y = *reinterpret_cast<const unsigned*>(&hi);
+  reinterpret_cast<uint2*>(base)[idx4] = o;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// CH = C / 128 float4 chunks per lane (lane owns elements (k*32 + lane)*4 .. +3)
+template <typename XT, typename RT, int CH>
+__global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ r,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, float eps,
+                                                                     float* __restrict__ y, float* __restrict__ mean_out,
+                                                                     float* __restrict__ rstd_out, long long N) {
+  constexpr int C = CH * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (row >= N) return;
+  float4 s[CH];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const long long i4 = row * (C / 4) + k * 32 + lane;
+    const float4 a = load4<XT>(x, i4), b = load4<RT>(r, i4);
+    s[k] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    sum += (s[k].x + s[k].y) + (s[k].z + s[k].w);
+  }
+  const float mean = warp_sum(sum) * (1.f / C);
+  float var = 0.f;
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const float dx = s[k].x - mean, dy = s[k].y - mean, dz = s[k].z - mean, dw = s[k].w - mean;
+    var += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(var) * (1.f / C) + eps);
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const int c4 = k * 32 + lane;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4), bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 o;
+    o.x = (s[k].x - mean) * rstd * g.x + bt.x;
+    o.y = (s[k].y - mean) * rstd * g.y + bt.y;
+    o.z = (s[k].z - mean) * rstd * g.z + bt.z;
+    o.w = (s[k].w - mean) * rstd * g.w + bt.w;
+    reinterpret_cast<float4*>(y)[row * (C / 4) + c4] = o;
+  }
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+template <typename XT, typename RT, int CH, bool LOWP>
+__global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x,
+                                                                     const void* __restrict__ r,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ mean_in,
+                                                                     const float* __restrict__ rstd_in,
+                                                                     float* __restrict__ ds, void* __restrict__ ds_lowp,
+                                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                     long long N, int rows_per_block) {
+  constexpr int C = CH * 128;
+  __shared__ float4 sg[kRowsPerBlock][CH * 32], sb[kRowsPerBlock][CH * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 accg[CH], accb[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) accg[k] = accb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  const long long row1 = row0 + rows_per_block < N ? row0 + rows_per_block : N;
+  for (long long row = row0 + warp; row < row1; row += kRowsPerBlock) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float4 xh[CH], g[CH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int c4 = k * 32 + lane;
+      const long long i4 = row * (C / 4) + c4;
+      const float4 a = load4<XT>(x, i4), b = load4<RT>(r, i4);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + i4);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+      xh[k] = make_float4((a.x + b.x - mean) * rstd, (a.y + b.y - mean) * rstd, (a.z + b.z - mean) * rstd,
+                          (a.w + b.w - mean) * rstd);
+      g[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+      s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+      accg[k].x += d.x * xh[k].x; accg[k].y += d.y * xh[k].y; accg[k].z += d.z * xh[k].z; accg[k].w += d.w * xh[k].w;
+      accb[k].x += d.x; accb[k].y += d.y; accb[k].z += d.z; accb[k].w += d.w;
+    }
+    const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const long long i4 = row * (C / 4) + k * 32 + lane;
+      float4 o;
+      o.x = rstd * (g[k].x - m1 - xh[k].x * m2);
+      o.y = rstd * (g[k].y - m1 - xh[k].y * m2);
+      o.z = rstd * (g[k].z - m1 - xh[k].z * m2);
+      o.w = rstd * (g[k].w - m1 - xh[k].w * m2);
+      reinterpret_cast<float4*>(ds)[i4] = o;
+      if (LOWP) store4_bf16(ds_lowp, i4, o);
+    }
+  }
+  // block-level reduction of the gamma / beta partials, then one fp32 atomic per channel and block
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    sg[warp][k * 32 + lane] = accg[k];
+    sb[warp][k * 32 + lane] = accb[k];
+  }
+  __syncthreads();
+  for (int c4 = threadIdx.x; c4 < CH * 32; c4 += kThreads) {
+    float4 tg = sg[0][c4], tb = sb[0][c4];
+#pragma unroll
+    for (int w = 1; w < kRowsPerBlock; ++w) {
+      const float4 a = sg[w][c4], b = sb[w][c4];
+      tg.x += a.x; tg.y += a.y; tg.z += a.z; tg.w += a.w;
+      tb.x += b.x; tb.y += b.y; tb.z += b.z; tb.w += b.w;
+    }
+    atomicAdd(dgamma + c4 * 4 + 0, tg.x); atomicAdd(dgamma + c4 * 4 + 1, tg.y);
+    atomicAdd(dgamma + c4 * 4 + 2, tg.z); atomicAdd(dgamma + c4 * 4 + 3, tg.w);
+    atomicAdd(dbeta + c4 * 4 + 0, tb.x); atomicAdd(dbeta + c4 * 4 + 1, tb.y);
+    atomicAdd(dbeta + c4 * 4 + 2, tb.z); atomicAdd(dbeta + c4 * 4 + 3, tb.w);
+  }
+}
+
+template <int CH>
+int launch_fwd_ch(int xd, int rd, const void* x, const void* r, const float* gamma, const float* beta, float eps, float* y,
+                  float* mean, float* rstd, long long N, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((N + kRowsPerBlock - 1) / kRowsPerBlock);
+  using bf = __nv_bfloat16;
+  if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32)
+    add_layernorm_fwd_kernel<bf, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+  else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32)
+    add_layernorm_fwd_kernel<float, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+  else if (xd == MSDA_B200_BF16 && rd == MSDA_B200_BF16)
+    add_layernorm_fwd_kernel<bf, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+  else
+    add_layernorm_fwd_kernel<float, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
+}
+
+template <int CH>
+int launch_bwd_ch(int xd, int rd, const float* dy, const void* x, const void* r, const float* gamma, const float* mean,
+                  const float* rstd, float* ds, void* ds_lowp, float* dgamma, float* dbeta, long long N, cudaStream_t st) {
+  // ~4 blocks per SM; each block walks a contiguous range of rows so the gamma/beta partials stay in registers
+  long long blocks = 148 * 4;
+  if (blocks > (N + kRowsPerBlock - 1) / kRowsPerBlock) blocks = (N + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int rows_per_block = (int)((N + blocks - 1) / blocks);
+  blocks = (N + rows_per_block - 1) / rows_per_block;
+  using bf = __nv_bfloat16;
+#define MSDA_LN_BWD(XT, RT)                                                                                       \
+  do {                                                                                                            \
+    if (ds_lowp)                                                                                                  \
+      add_layernorm_bwd_kernel<XT, RT, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(                          \
+          dy, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                            \
+    else                                                                                                          \
+      add_layernorm_bwd_kernel<XT, RT, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(                         \
+          dy, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                            \
+  } while (0)
+  if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32) MSDA_LN_BWD(bf, float);
+  else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32) MSDA_LN_BWD(float, float);
+  else if (xd == MSDA_B200_BF16 && rd == MSDA_B200_BF16) MSDA_LN_BWD(bf, bf);
+  else MSDA_LN_BWD(float, bf);
+#undef MSDA_LN_BWD
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
+}
+
+bool bad_dtype(int d) { return d != MSDA_B200_F32 && d != MSDA_B200_BF16; }
+
+}  // namespace
+
+extern "C" {
+
+int msda_b200_add_layernorm_forward(const void* x, int x_dtype, const void* residual, int residual_dtype,
+                                    const float* gamma, const float* beta, float eps, float* y, float* mean,
+                                    float* rstd, int64_t rows, int32_t channels, void* stream) {
+  if (rows < 0 || channels <= 0 || channels % 128 != 0 || channels > kMaxC)
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: channels must be a multiple of 128, at most 512");
+  if (bad_dtype(x_dtype) || bad_dtype(residual_dtype))
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: dtype must be 0 (f32) or 1 (bf16)");
+  if (rows == 0) return MSDA_B200_OK;
+  if (!x || !residual || !gamma || !beta || !y || !mean || !rstd)
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_forward: NULL tensor pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (channels / 128) {
+    case 1: return launch_fwd_ch<1>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
+    case 2: return launch_fwd_ch<2>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
+    case 4: return launch_fwd_ch<4>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
+  }
+  return MSDA_B200_ERR_UNSUPPORTED;
+}
+
+int msda_b200_add_layernorm_backward(const float* grad_y, const void* x, int x_dtype, const void* residual,
+                                     int residual_dtype, const float* gamma, const float* mean, const float* rstd,
+                                     float* grad_sum, void* grad_sum_lowp, float* grad_gamma, float* grad_beta,
+                                     int64_t rows, int32_t channels, void* stream) {
+  if (rows < 0 || channels <= 0 || channels % 128 != 0 || channels > kMaxC)
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: channels must be a multiple of 128, at most 512");
+  if (bad_dtype(x_dtype) || bad_dtype(residual_dtype))
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: dtype must be 0 (f32) or 1 (bf16)");
+  if (!grad_gamma || !grad_beta)
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_backward: NULL gamma/beta gradient");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(grad_gamma, 0, sizeof(float) * channels, st) != cudaSuccess) return MSDA_B200_ERR_CUDA;
+  if (cudaMemsetAsync(grad_beta, 0, sizeof(float) * channels, st) != cudaSuccess) return MSDA_B200_ERR_CUDA;
+  if (rows == 0) return MSDA_B200_OK;
+  if (!grad_y || !x || !residual || !gamma || !mean || !rstd || !grad_sum)
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_backward: NULL tensor pointer");
+  switch (channels / 128) {
+    case 1: return launch_bwd_ch<1>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 2: return launch_bwd_ch<2>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 4: return launch_bwd_ch<4>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+  }
+  return MSDA_B200_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -216,21 +216,42 @@ __device__ __forceinline__ void softmax_stats(const AT* lg, int LP, float& mx, f
   inv = 1.f / sum;
 }
 
-// softmax of the tile's (query, head) rows into shared memory, one thread per query
+// max and 1/sum(exp(x - max)) of one (query, head) row, computed by four adjacent lanes (lane & 3 = sub) that each
+// take every fourth logit; every lane of the warp must call it (full-mask shuffles), `valid` masks idle rows
+template <typename AT>
+__device__ __forceinline__ void softmax_stats_x4(const AT* lg, int LP, int sub, bool valid, float& mx, float& inv) {
+  mx = -INFINITY;
+  if (valid)
+    for (int s = sub; s < LP; s += 4) mx = fmaxf(mx, to_float<AT>(lg[s]));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  float sum = 0.f;
+  if (valid)
+    for (int s = sub; s < LP; s += 4) sum += expf(to_float<AT>(lg[s]) - mx);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  inv = valid ? 1.f / sum : 0.f;
+}
+
+// softmax of the tile's (query, head) rows into shared memory, four lanes per query
 template <typename AT, int NT>
 __device__ __forceinline__ void tile_softmax(const KParams& p, int b, int h, int q0, int nq, float* s_att, bool write_out) {
   const int LP = p.LP;
-  for (int ql = threadIdx.x; ql < nq; ql += NT) {
-    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+  const int sub = threadIdx.x & 3;
+  for (int qb = 0; qb < nq; qb += NT / 4) {
+    const int ql = qb + (threadIdx.x >> 2);
+    const bool valid = ql < nq;
+    const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
     const long long row = (((long long)b * p.Q + q) * p.H + h) * LP;
     const AT* lg = reinterpret_cast<const AT*>(p.logits) + row;
     float mx, inv;
-    softmax_stats<AT>(lg, LP, mx, inv);
-    for (int s = 0; s < LP; ++s) {
-      const float a = expf(to_float<AT>(lg[s]) - mx) * inv;
-      s_att[ql * LP + s] = a;
-      if (write_out && p.attn_out) p.attn_out[row + s] = a;
-    }
+    softmax_stats_x4<AT>(lg, LP, sub, valid, mx, inv);
+    if (valid)
+      for (int s = sub; s < LP; s += 4) {
+        const float a = expf(to_float<AT>(lg[s]) - mx) * inv;
+        s_att[ql * LP + s] = a;
+        if (write_out && p.attn_out) p.attn_out[row + s] = a;
+      }
   }
 }
 
@@ -752,6 +773,9 @@ int run_backward(const msda_b200_desc* desc, KParams p, void* grad_value, void* 
 }  // namespace
 
 extern "C" {
+
+// shared with layer_epilogue.cu (not part of the public header)
+int msda_b200_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 
 int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
 

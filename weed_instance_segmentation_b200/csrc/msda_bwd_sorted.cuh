@@ -131,14 +131,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
   };
   fetch_level(0);
   if (FUSED) {
-    // softmax statistics of every (query, head) row of the tile; visible after the first barrier of the level loop
-    for (int ql = tid; ql < TQ; ql += NT) {
-      float mx = 0.f, inv = 0.f;
-      if (ql < nq) {
-        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
-        softmax_stats<AT>(reinterpret_cast<const AT*>(p.logits) + (((long long)b * p.Q + q) * p.H + h) * p.LP, p.LP, mx, inv);
-      }
-      s_max[ql] = mx; s_inv[ql] = inv; s_dsum[ql] = 0.f;
+    // softmax statistics of every (query, head) row of the tile (four lanes per row); visible after the first
+    // barrier of the level loop
+    for (int qb = 0; qb < TQ; qb += NT / 4) {
+      const int ql = qb + (tid >> 2);
+      const bool valid = ql < nq;
+      const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
+      float mx, inv;
+      softmax_stats_x4<AT>(reinterpret_cast<const AT*>(p.logits) + (((long long)b * p.Q + q) * p.H + h) * p.LP, p.LP,
+                           tid & 3, valid, mx, inv);
+      if ((tid & 3) == 0) { s_max[ql] = valid ? mx : 0.f; s_inv[ql] = inv; s_dsum[ql] = 0.f; }
     }
   }
 

@@ -1,0 +1,80 @@
+"""Fused residual-add + LayerNorm for the pixel-decoder encoder layer.
+
+``add_layer_norm(x, residual, weight, bias, eps)`` computes ``F.layer_norm(residual + x, (C,), weight, bias, eps)``
+-- the two lines M2F:1049-1050 (and M2F:1058-1059) -- in one kernel per direction
+(``csrc/layer_epilogue.cu``). The output is float32, which is what ``F.layer_norm`` returns under autocast; ``x`` is
+typically the bfloat16 output of a projection and ``residual`` the float32 hidden state.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+_DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() else None
+
+
+class AddLayerNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps):
+        lib = _cabi.load()
+        C = x.shape[-1]
+        xc, rc = x.contiguous(), residual.contiguous()
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        rows = xc.numel() // C
+        y = torch.empty(xc.shape, dtype=torch.float32, device=xc.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.msda_b200_add_layernorm_forward(_ptr(xc), _DTYPE_CODE[xc.dtype], _ptr(rc), _DTYPE_CODE[rc.dtype],
+                                                            _ptr(w), _ptr(b), float(eps), _ptr(y), _ptr(mean), _ptr(rstd),
+                                                            rows, C, stream))
+        ctx.save_for_backward(xc, rc, w, mean, rstd)
+        ctx.param_dtypes = (weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_y):
+        lib = _cabi.load()
+        x, r, w, mean, rstd = ctx.saved_tensors
+        C = x.shape[-1]
+        rows = x.numel() // C
+        gy = grad_y.float().contiguous()
+        ds = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        need_lowp = x.dtype == torch.bfloat16 or r.dtype == torch.bfloat16
+        ds_lowp = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if need_lowp else None
+        gw = torch.empty(C, dtype=torch.float32, device=x.device)
+        gb = torch.empty(C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.msda_b200_add_layernorm_backward(_ptr(gy), _ptr(x), _DTYPE_CODE[x.dtype], _ptr(r),
+                                                             _DTYPE_CODE[r.dtype], _ptr(w), _ptr(mean), _ptr(rstd), _ptr(ds),
+                                                             _ptr(ds_lowp), _ptr(gw), _ptr(gb), rows, C, stream))
+        gx = ds_lowp if x.dtype == torch.bfloat16 else ds
+        gr = ds_lowp if r.dtype == torch.bfloat16 else ds
+        wd, bd = ctx.param_dtypes
+        return gx, gr, gw.to(wd), gb.to(bd), None
+
+
+def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                   eps: float = 1e-5) -> torch.Tensor:
+    """``F.layer_norm(residual + x, (C,), weight, bias, eps)`` in one kernel; float32 output.
+
+    ``x`` and ``residual``: same shape ``(..., C)``, float32 or bfloat16, CUDA; ``C`` a multiple of 128, at most 512.
+    """
+    if not (x.is_cuda and residual.is_cuda):
+        raise RuntimeError("add_layer_norm: tensors must live on a CUDA device (this package has no CPU fallback)")
+    if x.shape != residual.shape:
+        raise ValueError(f"add_layer_norm: x {tuple(x.shape)} and residual {tuple(residual.shape)} differ")
+    if x.dtype not in _DTYPE_CODE or residual.dtype not in _DTYPE_CODE:
+        raise TypeError("add_layer_norm: float32 or bfloat16 inputs only")
+    C = x.shape[-1]
+    if weight.numel() != C or bias.numel() != C:
+        raise ValueError("add_layer_norm: weight / bias must have C elements")
+    return AddLayerNormFunction.apply(x, residual, weight, bias, eps)

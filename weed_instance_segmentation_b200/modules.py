@@ -22,6 +22,7 @@ from torch import nn
 
 from .functional import ms_deform_attn
 from .fused import ms_deform_attn_fused
+from .layer_norm import add_layer_norm
 
 
 class MSDeformAttn(nn.Module):
@@ -142,6 +143,7 @@ class EncoderLayer(nn.Module):
         self.fc1 = nn.Linear(embed_dim, ffn_dim)
         self.fc2 = nn.Linear(ffn_dim, embed_dim)
         self.final_layer_norm = nn.LayerNorm(embed_dim)
+        self.fused_norm = False  # fused residual + LayerNorm kernels (layer_norm.py); convert_pixel_decoder() enables it
 
     @classmethod
     def from_hf(cls, layer: nn.Module) -> "EncoderLayer":
@@ -156,8 +158,18 @@ class EncoderLayer(nn.Module):
         new.activation_dropout = layer.activation_dropout
         new.fc1, new.fc2 = layer.fc1, layer.fc2
         new.final_layer_norm = layer.final_layer_norm
+        new.fused_norm = False
         new.train(layer.training)
         return new
+
+    def _add_norm(self, branch, residual, norm):
+        """``norm(residual + branch)`` (M2F:1049-1050, 1058-1059); one fused kernel when ``fused_norm`` is set."""
+        ok = (self.fused_norm and branch.is_cuda and branch.shape[-1] % 128 == 0 and branch.shape[-1] <= 512
+              and branch.dtype in (torch.float32, torch.bfloat16) and residual.dtype in (torch.float32, torch.bfloat16)
+              and (torch.is_autocast_enabled() or (branch.dtype == residual.dtype == torch.float32)))
+        if ok:
+            return add_layer_norm(branch, residual, norm.weight, norm.bias, norm.eps)
+        return norm(residual + branch)
 
     def forward(
         self,
@@ -182,14 +194,14 @@ class EncoderLayer(nn.Module):
             output_attentions=output_attentions,
         )
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
-        hidden_states = self.self_attn_layer_norm(residual + hidden_states)
+        hidden_states = self._add_norm(hidden_states, residual, self.self_attn_layer_norm)
 
         residual = hidden_states
         hidden_states = self.activation_fn(self.fc1(hidden_states))
         hidden_states = F.dropout(hidden_states, p=self.activation_dropout, training=self.training)
         hidden_states = self.fc2(hidden_states)
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
-        hidden_states = self.final_layer_norm(residual + hidden_states)
+        hidden_states = self._add_norm(hidden_states, residual, self.final_layer_norm)
 
         if self.training:
             # The reference clamps only `if not torch.isfinite(hidden_states).all()` (M2F:1062-1065), a
@@ -205,7 +217,8 @@ class EncoderLayer(nn.Module):
         return outputs
 
 
-def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fused_prologue: bool = True) -> int:
+def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fused_prologue: bool = True,
+                          fused_norm: bool = True) -> int:
     """Replace every HF pixel-decoder encoder layer (and its MSDeformAttn) inside ``model`` by the
     mirrors above, sharing parameters. Returns the number of layers converted.
 
@@ -223,6 +236,7 @@ def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fuse
                 new = EncoderLayer.from_hf(layer)
                 new.self_attn.assume_no_padding = assume_no_padding
                 new.self_attn.fused_prologue = fused_prologue
+                new.fused_norm = fused_norm
                 module.layers[i] = new
                 converted += 1
     return converted
