@@ -223,8 +223,6 @@ class Problem:
         self.flags = _cabi.FLAG_BF16_ATOMICS if (functional._BF16_ATOMICS and dtype == "bf16") else 0
         if functional._BWD_V1:
             self.flags |= _cabi.FLAG_BWD_V1
-        if functional._BWD_TQ256:
-            self.flags |= _cabi.FLAG_BWD_TQ256
         self.desc, self._keep = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi, self.flags)
         self.pdesc, self._keep2 = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi,
                                                   self.flags | _cabi.FLAG_PROFILE)

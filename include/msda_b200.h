@@ -65,7 +65,6 @@ extern "C" {
                                          /* bf16x2 atomics in place (no fp32 workspace, lossy)   */
 #define MSDA_B200_FLAG_BWD_V1 4u         /* backward: force the per-corner reduction kernel (v1)  */
                                          /* instead of the pixel-sorted kernel (v2, D=32 & P=4)  */
-#define MSDA_B200_FLAG_BWD_TQ256 8u      /* backward v2 tuning: 256 queries / 512 threads per block */
 
 /* Problem description: plain old data, filled by the caller on the host. */
 typedef struct msda_b200_desc {

@@ -40,7 +40,6 @@ _TILE = _parse_tile(os.environ.get("MSDA_B200_TILE", "8x16"))
 _USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "1") != "0"
 _BF16_ATOMICS = os.environ.get("MSDA_B200_BF16_ATOMICS", "0") == "1"
 _BWD_V1 = os.environ.get("MSDA_B200_BWD_V1", "0") == "1"
-_BWD_TQ256 = os.environ.get("MSDA_B200_BWD_TQ256", "0") == "1"
 
 _order_cache: dict = {}
 _lsi_checked: set = set()
@@ -178,8 +177,6 @@ class MSDeformAttnFunction(torch.autograd.Function):
             flags |= _cabi.FLAG_BF16_ATOMICS
         if _BWD_V1:
             flags |= _cabi.FLAG_BWD_V1
-        if _BWD_TQ256:
-            flags |= _cabi.FLAG_BWD_TQ256
         desc, keep = _cabi.make_desc(B, S, Q, H, D, L, P, _DTYPE_CODE[value.dtype], _DTYPE_CODE[attn.dtype],
                                      shapes, level_start, flags)
         grad_value = torch.empty_like(value)
