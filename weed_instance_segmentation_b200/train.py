@@ -178,18 +178,25 @@ def inference_throughput(model, device, args, rank: int) -> float:
         with torch.no_grad(), amp:
             return model(pixel_values=pixel_values)
 
+    cuda = device.type == "cuda"
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
+    if cuda:
+        torch.cuda.synchronize()
     if multi:
         dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    if cuda:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-    e1.record()
-    torch.cuda.synchronize()
-    secs = e0.elapsed_time(e1) / 1e3
+    if cuda:
+        e1.record()
+        torch.cuda.synchronize()
+        secs = e0.elapsed_time(e1) / 1e3
+    else:
+        secs = time.perf_counter() - t0  # the reference's CPU-runnable case (BASELINE config 1)
     if multi:
         dist.barrier()
         t = torch.tensor([secs], dtype=torch.float64, device=device)
