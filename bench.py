@@ -315,6 +315,11 @@ def run_b200(args, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    if local_rank == 0:
+        from weed_instance_segmentation_b200 import build as _build
+        _build.build()  # no-op when the in-tree library is current
+    if world > 1:
+        dist.barrier()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
 

@@ -77,7 +77,8 @@ CASES = [
 @pytest.fixture(scope="module")
 def wis():
     import weed_instance_segmentation_b200 as w
-    from weed_instance_segmentation_b200 import _cabi
+    from weed_instance_segmentation_b200 import _cabi, build
+    build.build()  # no-op when libmsda_b200.so is current; the product itself never builds or falls back
     _cabi.load()
     return w
 

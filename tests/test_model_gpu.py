@@ -17,7 +17,8 @@ CFG = dict(decoder_layers=4, encoder_layers=6, num_queries=20, train_num_points=
 @pytest.fixture(scope="module")
 def models():
     pytest.importorskip("transformers")
-    from weed_instance_segmentation_b200 import _cabi, train
+    from weed_instance_segmentation_b200 import _cabi, build, train
+    build.build()
     _cabi.load()
     ref = train.build_model("swin_tiny_test", num_labels=3, seed=0, **CFG).cuda()
     # A freshly initialised module has zero offset weights and integer-pixel biases (M2F:2116-2128), so every

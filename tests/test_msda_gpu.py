@@ -20,7 +20,8 @@ BF16_BAR = 2e-2
 @pytest.fixture(scope="module")
 def wis():
     import weed_instance_segmentation_b200 as w
-    from weed_instance_segmentation_b200 import _cabi
+    from weed_instance_segmentation_b200 import _cabi, build
+    build.build()  # no-op when libmsda_b200.so is current; the product itself never builds or falls back
     _cabi.load()  # fail loudly if the extension is missing
     assert torch.cuda.is_available()
     return w
