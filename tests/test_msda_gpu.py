@@ -141,6 +141,44 @@ def test_random_bf16(wis, case, dist, attn_dtype):
                   safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
 
 
+# Geometries that stress the pixel-sorted backward's window logic (D=32, P=4, bf16 -> msda_bwd_sorted_kernel):
+# levels wider than the 256-pixel window edge, bounding boxes far larger than the 2048-pixel window capacity
+# (everything outside takes the fallback route), Q != S so queries arrive in no spatial order, one and five levels.
+SORTED_CASES = [
+    ("wide_levels", 1, [(12, 300), (256, 20)], 8, 32, 4, 500),
+    ("c5_like", 1, [(64, 64), (128, 128), (256, 256)], 2, 32, 4, 3000),
+    ("one_level", 2, [(40, 40)], 8, 32, 4, None),
+    ("five_levels", 1, [(3, 3), (5, 5), (9, 9), (17, 17), (33, 33)], 4, 32, 4, None),
+]
+
+
+@pytest.mark.parametrize("dist", ["init", "trained", "adversarial"])
+@pytest.mark.parametrize("case", SORTED_CASES, ids=[c[0] for c in SORTED_CASES])
+def test_sorted_backward_windows(wis, case, dist):
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    tag, B, shapes, H, D, P, Q = case
+    x = msda_inputs(B, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=21, num_queries=Q,
+                    value_dtype=torch.bfloat16)
+    args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    _assert_close(_run(wis, *args), _oracle(*args), BF16_BAR, f"{tag}/{dist}",
+                  safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
+
+
+def test_sorted_and_per_corner_backward_agree(wis, monkeypatch):
+    """v2 (pixel-sorted) and v1 (per-corner reductions) differ only in fp32 summation order."""
+    from weed_instance_segmentation_b200 import functional as F
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    shapes = [(16, 16), (32, 32), (64, 64)]
+    x = msda_inputs(2, shapes, dist="trained", seed=13, value_dtype=torch.bfloat16)
+    args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+    v2 = _run(wis, *args)
+    monkeypatch.setattr(F, "_BWD_V1", True)
+    v1 = _run(wis, *args)
+    assert np.array_equal(v1[0], v2[0])
+    for name, a, b in zip(("grad_value", "grad_loc", "grad_attn"), v1[1:], v2[1:]):
+        assert rel_err(a, b) <= 1e-2, name  # both carry one bf16 rounding of the output
+
+
 def test_query_order_does_not_change_results(wis, monkeypatch):
     from weed_instance_segmentation_b200 import functional as F
     from weed_instance_segmentation_b200.synth import msda_inputs
