@@ -219,23 +219,35 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
       }
     }
 
-    // ---- c: histogram over window pixels; contributions outside the window go to the fallback list
-    for (int id = tid; id < NC; id += NT) {
-      const int si = id >> 2, cn = id & 3;
+    // ---- c: histogram over window pixels; contributions outside the window go to the fallback list.
+    // One thread per *sample*: its four corners share the descriptor loads; the window code of every corner
+    // ((py << 8) | px, -1 = inactive, -2 = fallback) stays in registers for the fill pass (e).
+    int code[SPT][4];
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int si = r * NT + tid;
       const float4 w = s_w[si];
       const int xy = s_xy[si];
       const int gcode = xy >> 24;
-      const bool xa = ((cn & 1) ? w.y : w.x) != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
-      const bool ya = ((cn & 2) ? w.w : w.z) != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
-      if (xa && ya) {
-        const int px = (xy & 0xfff) + ((cn & 1) ? dxs : 0) - x0, py = ((xy >> 12) & 0xfff) + ((cn & 2) ? dys : 0) - y0;
-        if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
-          atomicAdd(&s_cnt[py * ww + px], 1);
-        } else {
-          s_fb_end[-1 - atomicAdd(&s_misc[MI_FBN], 1)] = (unsigned short)id;
+      const bool xa0 = w.x != 0.f || (gcode & 3) != 1, xa1 = w.y != 0.f || ((gcode >> 2) & 3) != 1;
+      const bool ya0 = w.z != 0.f || ((gcode >> 4) & 3) != 1, ya1 = w.w != 0.f || ((gcode >> 6) & 3) != 1;
+      const int bx = (xy & 0xfff) - x0, by = ((xy >> 12) & 0xfff) - y0;
+      *reinterpret_cast<float4*>(&s_dot[si * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);  // active corners are overwritten in f / g
+#pragma unroll
+      for (int cn = 0; cn < 4; ++cn) {
+        const bool active = ((cn & 1) ? xa1 : xa0) && ((cn & 2) ? ya1 : ya0);
+        const int px = bx + ((cn & 1) ? dxs : 0), py = by + ((cn & 2) ? dys : 0);
+        int cd = -1;
+        if (active) {
+          if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
+            cd = (py << 8) | px;
+            atomicAdd(&s_cnt[py * ww + px], 1);
+          } else {
+            cd = -2;
+            s_fb_end[-1 - atomicAdd(&s_misc[MI_FBN], 1)] = (unsigned short)(si * 4 + cn);
+          }
         }
-      } else {
-        s_dot[id] = 0.f;
+        code[r][cn] = cd;
       }
     }
     __syncthreads();
@@ -284,20 +296,20 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
     }
     __syncthreads();
 
-    // ---- e: fill (counting sort by window pixel)
-    for (int id = tid; id < NC; id += NT) {
-      const int si = id >> 2, cn = id & 3;
+    // ---- e: fill (counting sort by window pixel), from the codes kept in registers
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int si = r * NT + tid;
       const float4 w = s_w[si];
-      const int xy = s_xy[si];
-      const int gcode = xy >> 24;
-      const float wx = (cn & 1) ? w.y : w.x, wy = (cn & 2) ? w.w : w.z;
-      const bool xa = wx != 0.f || ((gcode >> ((cn & 1) * 2)) & 3) != 1;
-      const bool ya = wy != 0.f || ((gcode >> (4 + (cn >> 1) * 2)) & 3) != 1;
-      if (xa && ya) {
-        const int px = (xy & 0xfff) + ((cn & 1) ? dxs : 0) - x0, py = ((xy >> 12) & 0xfff) + ((cn & 2) ? dys : 0) - y0;
-        if ((unsigned)px < (unsigned)ww && (unsigned)py < (unsigned)wh) {
-          const int slot = atomicAdd(&s_cnt[py * ww + px], 1);
-          s_ent[slot] = make_int2((py << 24) | (px << 16) | id, __float_as_int(s_a[si] * wy * wx));
+      const float a = s_a[si];
+      const float wy0 = a * w.z, wy1 = a * w.w;
+#pragma unroll
+      for (int cn = 0; cn < 4; ++cn) {
+        const int cd = code[r][cn];
+        if (cd >= 0) {
+          const int slot = atomicAdd(&s_cnt[(cd >> 8) * ww + (cd & 0xff)], 1);
+          s_ent[slot] = make_int2((cd << 16) | (si * 4 + cn),
+                                  __float_as_int(((cn & 2) ? wy1 : wy0) * ((cn & 1) ? w.y : w.x)));
         }
       }
     }
