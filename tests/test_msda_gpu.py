@@ -319,3 +319,28 @@ def test_full_size_matches_reference_on_gpu_bf16(wis):
             e = ((got.float() - want).abs().max() / want.abs().max()).item()
             assert e <= BF16_BAR, f"batch {b0}: {name} rel err {e:.3e}"
         del rv, rl, ra, ro
+
+
+def test_sorted_backward_fuzz(wis):
+    """40 random geometries / location patterns (tools/fuzz_sorted_backward.py): v2 and v1 agree to summation order."""
+    import importlib.util
+    import os
+    from weed_instance_segmentation_b200 import functional as F
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fuzz_sorted_backward.py")
+    spec = importlib.util.spec_from_file_location("fuzz_sorted_backward", path)
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    rng = np.random.default_rng(123)
+    try:
+        for i in range(40):
+            B, shapes, H, Q, dist = fz.random_case(rng)
+            value, loc, attn, go = fz.make_inputs(B, shapes, H, Q, dist, rng)
+            F._BWD_V1 = False
+            v2 = fz.run(value, shapes, loc, attn, go)
+            F._BWD_V1 = True
+            v1 = fz.run(value, shapes, loc, attn, go)
+            assert torch.equal(v1[0], v2[0])
+            assert fz.rel(v2[1], v1[1]) <= 1.6e-2 and fz.rel(v2[3], v1[3]) <= 1.6e-2, (i, shapes, dist)
+            assert fz.rel(v2[2], v1[2]) <= 1e-4, (i, shapes, dist)
+    finally:
+        F._BWD_V1 = False
