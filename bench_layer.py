@@ -8,6 +8,7 @@ Compares, with identical weights and inputs:
   modules   : modules.EncoderLayer + MSDeformAttn, un-fused prologue
   fused     : modules.EncoderLayer + MSDeformAttn with the fused softmax/location prologue
   fused+norm: the same plus the fused residual + LayerNorm kernels (layer_norm.py)
+  fused+norm+linear: the same plus projections with the fused bias-gradient reduction (linear.py)
 
     python bench_layer.py [--amp bf16|none] [--steps K] [--warmup W] [--batch B]
 Prints one JSON line.
@@ -62,11 +63,12 @@ def main():
 
     def variant(name):
         layer = copy.deepcopy(ref_layer)
-        if name in ("modules", "fused", "fused+norm"):
+        if name in ("modules", "fused", "fused+norm", "fused+norm+linear"):
             layer = modules.EncoderLayer.from_hf(layer)
             layer.self_attn.assume_no_padding = True
             layer.self_attn.fused_prologue = name != "modules"
-            layer.fused_norm = name == "fused+norm"
+            layer.fused_norm = name in ("fused+norm", "fused+norm+linear")
+            layer.fused_linear = layer.self_attn.fused_linear = name == "fused+norm+linear"
         return layer
 
     def run(layer, patched):
@@ -101,13 +103,14 @@ def main():
         return timed()
 
     results, outs = {}, {}
-    for name, patched in (("reference", False), ("function", True), ("modules", True), ("fused", True), ("fused+norm", True)):
+    for name, patched in (("reference", False), ("function", True), ("modules", True), ("fused", True), ("fused+norm", True),
+                          ("fused+norm+linear", True)):
         ms, out, gx = run(variant(name), patched)
         results[name] = {"ms_per_layer_fwd_bwd": ms}
         outs[name] = (out, gx)
         torch.cuda.empty_cache()
     r_out, r_gx = outs["reference"]
-    for name in ("function", "modules", "fused", "fused+norm"):
+    for name in ("function", "modules", "fused", "fused+norm", "fused+norm+linear"):
         o, g = outs[name]
         results[name]["out_rel_err_vs_reference"] = ((o - r_out).abs().max() / r_out.abs().max()).item()
         results[name]["grad_input_rel_err_vs_reference"] = ((g - r_gx).abs().max() / r_gx.abs().max()).item()

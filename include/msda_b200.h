@@ -154,6 +154,14 @@ int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* x 
                                      int64_t rows, int32_t channels, void* stream);
 
 /*
+ * Column sum of a contiguous (rows x cols) matrix into float32 -- the bias gradient of a projection
+ * (grad_bias = sum over rows of grad_out).  cols a multiple of 8 (bf16) / 4 (f32), at most 2048 / 1024.
+ * The library zero-fills `out` first.
+ */
+int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev, cols*/, int64_t rows, int32_t cols,
+                         void* stream);
+
+/*
  * Profiling aid for bench.py: when desc->flags has MSDA_B200_FLAG_PROFILE the library records
  * CUDA events on `stream` around each kernel it launches.  After the stream has been
  * synchronised, msda_b200_profile_ms(which, &ms) returns the device time of the last such launch

@@ -1,0 +1,62 @@
+"""Projection with the fused bias-gradient reduction (linear.py, msda_b200_column_sum) against F.linear."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    from weed_instance_segmentation_b200 import build
+    build.build()
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("rows", [1, 33, 5000, 172032])
+@pytest.mark.parametrize("cols", [8, 96, 192, 256, 1024])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_column_sum(rows, cols, dtype):
+    from weed_instance_segmentation_b200.linear import column_sum
+    if rows * cols > 60_000_000:
+        rows = 60_000_000 // cols
+    m = torch.randn(rows, cols, device="cuda").to(dtype)
+    got = column_sum(m)
+    want = m.double().sum(0)
+    assert got.dtype == torch.float32 and got.shape == (cols,)
+    assert ((got.double() - want).abs().max() / want.abs().max().clamp_min(1.0)).item() < 1e-5
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_linear_matches_torch(autocast):
+    from weed_instance_segmentation_b200.linear import linear
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(4, 1000, 256, device="cuda", generator=g)
+    w = (0.05 * torch.randn(192, 256, device="cuda", generator=g))
+    b = torch.randn(192, device="cuda", generator=g)
+    go = torch.randn(4, 1000, 192, device="cuda", generator=g)
+    res = {}
+    for name, fn in (("ref", F.linear), ("new", linear)):
+        xs, ws, bs = (t.clone().requires_grad_(True) for t in (x, w, b))
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = fn(xs, ws, bs)
+        y.backward(go.to(y.dtype))
+        res[name] = (y.detach().float(), xs.grad, ws.grad, bs.grad)
+    bar = 2e-2 if autocast else 1e-5
+    for a, c, nm in zip(res["new"], res["ref"], ("y", "grad_x", "grad_w", "grad_b")):
+        assert a.dtype == c.dtype and a.shape == c.shape
+        assert _rel(a, c) <= bar, (nm, _rel(a, c))
+    # the bias gradient itself is more accurate than torch's bf16 reduction: compare with fp64
+    gb64 = go.to(torch.bfloat16 if autocast else torch.float32).double().reshape(-1, 192).sum(0)
+    assert _rel(res["new"][3], gb64) <= (1e-5 if not autocast else 1e-5)
+
+
+def test_column_sum_errors():
+    from weed_instance_segmentation_b200 import MSDAError
+    from weed_instance_segmentation_b200.linear import column_sum
+    with pytest.raises(MSDAError):
+        column_sum(torch.zeros(4, 12, device="cuda", dtype=torch.bfloat16))  # 12 columns: not a multiple of 8
+    assert column_sum(torch.zeros(0, 16, device="cuda")).abs().sum().item() == 0

@@ -30,6 +30,7 @@ EXPORTS = (
     "msda_b200_backward_fused",
     "msda_b200_add_layernorm_forward",
     "msda_b200_add_layernorm_backward",
+    "msda_b200_column_sum",
     "msda_b200_profile_ms",
     "msda_b200_launch_count",
 )
@@ -91,6 +92,8 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_add_layernorm_backward.restype = ctypes.c_int
     lib.msda_b200_add_layernorm_backward.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_column_sum.restype = ctypes.c_int
+    lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_profile_ms.restype = ctypes.c_int
     lib.msda_b200_profile_ms.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.msda_b200_launch_count.restype = ctypes.c_int64

@@ -262,3 +262,94 @@ int msda_b200_add_layernorm_backward(const float* grad_y, const void* x, int x_d
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column sum of a (rows x cols) matrix into fp32: the bias gradient of a projection (grad_bias = sum_rows grad_out).
+// torch's generic reduce kernel needs ~110 us per projection at config 2 (172 032 rows); this one streams the
+// matrix once with 16-byte loads. cols must be a multiple of 8 (bf16) / 4 (fp32) and at most 2048.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename T>
+struct ColVec;
+template <>
+struct ColVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const void* base, long long idx, float (&f)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base) + idx);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+};
+template <>
+struct ColVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const void* base, long long idx, float (&f)[8]) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base) + idx);
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+};
+
+// block = (cv column vectors) x (rl row lanes); every thread walks rows r0 + ry, r0 + ry + rl, ...
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ m, float* __restrict__ out, long long rows,
+                                                     int cv /* cols / N */, int rl, int rows_per_block) {
+  constexpr int N = ColVec<T>::N;
+  extern __shared__ float s_part[];  // [rl][cv * N]
+  const int cx = threadIdx.x % cv, ry = threadIdx.x / cv;
+  float acc[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) acc[j] = 0.f;
+  if (ry < rl) {
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    for (long long r = r0 + ry; r < r1; r += rl) {
+      float f[N];
+      ColVec<T>::load(m, r * cv + cx, f);
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) s_part[(ry * cv + cx) * N + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cv * N; c += blockDim.x) {
+    float t = 0.f;
+    for (int y = 0; y < rl; ++y) t += s_part[y * cv * N + c];
+    atomicAdd(out + c, t);
+  }
+}
+
+}  // namespace
+
+extern "C" int msda_b200_column_sum(const void* matrix, int dtype, float* out, int64_t rows, int32_t cols, void* stream) {
+  if (bad_dtype(dtype)) return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "column_sum: dtype must be 0 (f32) or 1 (bf16)");
+  const int n = dtype == MSDA_B200_BF16 ? 8 : 4;
+  if (rows < 0 || cols <= 0 || cols % n != 0 || cols > 2048)
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "column_sum: cols must be a multiple of 8 (bf16) / 4 (f32), at most 2048");
+  if (!out) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "column_sum: NULL output");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(out, 0, sizeof(float) * cols, st) != cudaSuccess)
+    return msda_b200_internal_fail(MSDA_B200_ERR_CUDA, "column_sum: memset failed");
+  if (rows == 0) return MSDA_B200_OK;
+  if (!matrix) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "column_sum: NULL matrix");
+  const int cv = cols / n;  // 16-byte column vectors per row
+  if (cv > 256) return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "column_sum: too many columns");
+  const int rl = 256 / cv;  // rows walked in parallel by one block
+  const int threads = 256;
+  long long blocks = 148 * 8;
+  const long long min_rows = (long long)rl * 4;
+  if (blocks * min_rows > rows) blocks = (rows + min_rows - 1) / min_rows;
+  if (blocks < 1) blocks = 1;
+  const int rows_per_block = (int)((rows + blocks - 1) / blocks);
+  blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const size_t smem = sizeof(float) * (size_t)rl * cols;
+  if (dtype == MSDA_B200_BF16)
+    colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
+  else
+    colsum_kernel<float><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
+}

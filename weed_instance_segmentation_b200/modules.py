@@ -23,6 +23,7 @@ from torch import nn
 from .functional import ms_deform_attn
 from .fused import ms_deform_attn_fused
 from .layer_norm import add_layer_norm
+from .linear import linear as _fused_linear
 
 
 class MSDeformAttn(nn.Module):
@@ -48,6 +49,7 @@ class MSDeformAttn(nn.Module):
         self.assume_no_padding = False
         # Compute softmax and sampling locations inside the kernels (fused.py); convert_pixel_decoder() enables it.
         self.fused_prologue = False
+        self.fused_linear = False  # projections with the fused bias-gradient reduction (linear.py)
 
     @classmethod
     def from_hf(cls, mod: nn.Module) -> "MSDeformAttn":
@@ -62,8 +64,13 @@ class MSDeformAttn(nn.Module):
         new.output_proj = mod.output_proj
         new.assume_no_padding = False
         new.fused_prologue = False
+        new.fused_linear = False
         new.train(mod.training)
         return new
+
+    def _proj(self, layer: nn.Linear, x):
+        """``layer(x)``; with ``fused_linear`` the bias gradient is reduced by the B200 column-sum kernel."""
+        return _fused_linear(x, layer.weight, layer.bias) if self.fused_linear else layer(x)
 
     @staticmethod
     def with_pos_embed(tensor, position_embeddings):
@@ -92,19 +99,19 @@ class MSDeformAttn(nn.Module):
             )
         H, L, P = self.n_heads, self.n_levels, self.n_points
 
-        value = self.value_proj(encoder_hidden_states)
+        value = self._proj(self.value_proj, encoder_hidden_states)
         if attention_mask is not None and not self.assume_no_padding:
             value = value.masked_fill(attention_mask[..., None], float(0))
         value = value.view(batch_size, sequence_length, H, self.d_model // H)
-        sampling_offsets = self.sampling_offsets(hidden_states).view(batch_size, num_queries, H, L, P, 2)
-        attention_weights = self.attention_weights(hidden_states).view(batch_size, num_queries, H, L * P)
+        sampling_offsets = self._proj(self.sampling_offsets, hidden_states).view(batch_size, num_queries, H, L, P, 2)
+        attention_weights = self._proj(self.attention_weights, hidden_states).view(batch_size, num_queries, H, L * P)
         if self.fused_prologue and reference_points.shape[-1] == 2 and not reference_points.requires_grad:
             # softmax (M2F:955-960) and ref + off / (W, H) (M2F:962-971) happen inside the kernels
             res = ms_deform_attn_fused(value, spatial_shapes_list, level_start_index, sampling_offsets,
                                        attention_weights, reference_points,
                                        return_attention_weights=output_attentions)
             output, attention_weights = res if output_attentions else (res, None)
-            return self.output_proj(output), attention_weights
+            return self._proj(self.output_proj, output), attention_weights
         attention_weights = F.softmax(attention_weights, -1).view(batch_size, num_queries, H, L, P)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.tensor(
@@ -124,7 +131,7 @@ class MSDeformAttn(nn.Module):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but got {reference_points.shape[-1]}")
 
         output = ms_deform_attn(value, spatial_shapes_list, level_start_index, sampling_locations, attention_weights)
-        output = self.output_proj(output)
+        output = self._proj(self.output_proj, output)
         return output, attention_weights
 
 
@@ -144,6 +151,7 @@ class EncoderLayer(nn.Module):
         self.fc2 = nn.Linear(ffn_dim, embed_dim)
         self.final_layer_norm = nn.LayerNorm(embed_dim)
         self.fused_norm = False  # fused residual + LayerNorm kernels (layer_norm.py); convert_pixel_decoder() enables it
+        self.fused_linear = False
 
     @classmethod
     def from_hf(cls, layer: nn.Module) -> "EncoderLayer":
@@ -159,8 +167,12 @@ class EncoderLayer(nn.Module):
         new.fc1, new.fc2 = layer.fc1, layer.fc2
         new.final_layer_norm = layer.final_layer_norm
         new.fused_norm = False
+        new.fused_linear = False
         new.train(layer.training)
         return new
+
+    def _proj(self, layer: nn.Linear, x):
+        return _fused_linear(x, layer.weight, layer.bias) if self.fused_linear else layer(x)
 
     def _add_norm(self, branch, residual, norm):
         """``norm(residual + branch)`` (M2F:1049-1050, 1058-1059); one fused kernel when ``fused_norm`` is set."""
@@ -197,9 +209,9 @@ class EncoderLayer(nn.Module):
         hidden_states = self._add_norm(hidden_states, residual, self.self_attn_layer_norm)
 
         residual = hidden_states
-        hidden_states = self.activation_fn(self.fc1(hidden_states))
+        hidden_states = self.activation_fn(self._proj(self.fc1, hidden_states))
         hidden_states = F.dropout(hidden_states, p=self.activation_dropout, training=self.training)
-        hidden_states = self.fc2(hidden_states)
+        hidden_states = self._proj(self.fc2, hidden_states)
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
         hidden_states = self._add_norm(hidden_states, residual, self.final_layer_norm)
 
@@ -218,7 +230,7 @@ class EncoderLayer(nn.Module):
 
 
 def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fused_prologue: bool = True,
-                          fused_norm: bool = True) -> int:
+                          fused_norm: bool = True, fused_linear: bool = True) -> int:
     """Replace every HF pixel-decoder encoder layer (and its MSDeformAttn) inside ``model`` by the
     mirrors above, sharing parameters. Returns the number of layers converted.
 
@@ -237,6 +249,7 @@ def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fuse
                 new.self_attn.assume_no_padding = assume_no_padding
                 new.self_attn.fused_prologue = fused_prologue
                 new.fused_norm = fused_norm
+                new.fused_linear = new.self_attn.fused_linear = fused_linear
                 module.layers[i] = new
                 converted += 1
     return converted
