@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint4* __restrict__ s
     __syncthreads();
     base = sm;
   }
+  // mode 2: 8 lanes x 8 B per 64-byte chunk (LDG.64, 4 chunks per warp request)
+  // mode 3: 8 lanes x 16 B per 128-byte ALIGNED line (an fp32 head: 4 full lines per warp request)
   constexpr int LPG = MODE == 0 ? 4 : 8;
   const int lane = threadIdx.x % LPG;
   unsigned s = (blockIdx.x * 256 + threadIdx.x / LPG) * 2654435761u + 12345u;
@@ -33,7 +35,15 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint4* __restrict__ s
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int chunk = rng(s) & (window_chunks / 2 - 1);  // power-of-two window: no integer division in the loop
-      v[k] = SMEM ? base[chunk * 4 + lane] : __ldg(base + chunk * 4 + lane);
+      if (MODE == 2) {
+        const uint2 t = SMEM ? reinterpret_cast<const uint2*>(base)[chunk * 8 + lane]
+                             : __ldg(reinterpret_cast<const uint2*>(base) + chunk * 8 + lane);
+        v[k] = make_uint4(t.x, t.y, t.x, t.y);
+      } else if (MODE == 3) {
+        v[k] = SMEM ? base[(chunk & ~1) * 4 + lane] : __ldg(base + (chunk & ~1) * 4 + lane);
+      } else {
+        v[k] = SMEM ? base[chunk * 4 + lane] : __ldg(base + chunk * 4 + lane);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc += __uint_as_float(v[k].x) + __uint_as_float(v[k].w);
@@ -109,6 +119,12 @@ int main() {
   rep("LDG.128 128B pairs  (L1, 64KB window)", time_ms([&] { gather_kernel<1, false><<<grid, 256>>>(src, window, iters, sink); }));
   rep("LDS.128 64B chunks (smem 64KB)", time_ms([&] { gather_kernel<0, true><<<grid, 256, window * 64>>>(src, window, iters, sink); }));
   rep("LDS.128 128B pairs  (smem 64KB)", time_ms([&] { gather_kernel<1, true><<<grid, 256, window * 64>>>(src, window, iters, sink); }));
+  {
+    const double b2 = (double)grid * 256 * iters * 4 * 8;
+    float ms = time_ms([&] { gather_kernel<2, false><<<grid, 256>>>(src, window, iters, sink); });
+    printf("%-44s %8.3f ms  %8.1f GB/s  (%.1f B/clk/SM @1.965GHz)\n", "LDG.64 64B chunks, 8 lanes (L1, 64KB window)", ms, b2 / ms / 1e6, b2 / ms / 1e6 / sms / 1.965);
+  }
+  rep("LDG.128 aligned 128B lines (L1, 64KB window)", time_ms([&] { gather_kernel<3, false><<<grid, 256>>>(src, window, iters, sink); }));
   // smaller window: 16 KB
   rep("LDG.128 64B chunks (L1, 16KB window)", time_ms([&] { gather_kernel<0, false><<<grid, 256>>>(src, 256, iters, sink); }));
   // more CTAs per SM (occupancy 8)

@@ -147,6 +147,29 @@ struct Vec16<__nv_bfloat16> {
 
 __device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
 
+// Packed fp32 FMA (sm_100a FFMA2): (a0, a1) += w * (f0, f1) and (a0, a1) += (g0, g1) * (f0, f1), each element rounded
+// exactly like fmaf. One instruction for two FMAs: the kernels here are bound by instruction issue, not by the FMA pipe.
+__device__ __forceinline__ void fma2_scalar(float& a0, float& a1, float w, float f0, float f1) {
+  asm("{ .reg .b64 ra, rw, rf;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rw, {%2, %2};\n\t"
+      "mov.b64 rf, {%3, %4};\n\t"
+      "fma.rn.f32x2 ra, rw, rf, ra;\n\t"
+      "mov.b64 {%0, %1}, ra; }"
+      : "+f"(a0), "+f"(a1)
+      : "f"(w), "f"(f0), "f"(f1));
+}
+__device__ __forceinline__ void fma2_pair(float& a0, float& a1, float g0, float g1, float f0, float f1) {
+  asm("{ .reg .b64 ra, rg, rf;\n\t"
+      "mov.b64 ra, {%0, %1};\n\t"
+      "mov.b64 rg, {%2, %3};\n\t"
+      "mov.b64 rf, {%4, %5};\n\t"
+      "fma.rn.f32x2 ra, rg, rf, ra;\n\t"
+      "mov.b64 {%0, %1}, ra; }"
+      : "+f"(a0), "+f"(a1)
+      : "f"(g0), "f"(g1), "f"(f0), "f"(f1));
+}
+
 // red.global.add.v4.f32 (sm_90+): one 16-byte reduction, no return value.
 __device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -318,16 +341,16 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
         float f[VEC];
         Vec16<VT>::unpack(v00, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.x, f[j], acc[j]);
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.x, f[j], f[j + 1]);
         Vec16<VT>::unpack(v01, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.y, f[j], acc[j]);
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.y, f[j], f[j + 1]);
         Vec16<VT>::unpack(v10, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.z, f[j], acc[j]);
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.z, f[j], f[j + 1]);
         Vec16<VT>::unpack(v11, f);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w.w, f[j], acc[j]);
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
       }
     }
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;

@@ -376,17 +376,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
             for (int j = 0; j < VEC; ++j) acc[u][j] = 0.f;
           }
         }
-        float d = 0.f;
+        float d0 = 0.f, d1 = 0.f;  // even / odd channels (packed FFMA2)
 #pragma unroll
         for (int u = 0; u < CH; ++u) {
           float gf[VEC];
           Vec16<VT>::unpack(go_lane[(id >> (2 + LP2)) * LPP + u], gf);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            acc[u][j] = fmaf(wgt, gf[j], acc[u][j]);
-            d = fmaf(gf[j], vf[u][j], d);
+          for (int j = 0; j < VEC; j += 2) {
+            fma2_scalar(acc[u][j], acc[u][j + 1], wgt, gf[j], gf[j + 1]);
+            fma2_pair(d0, d1, gf[j], gf[j + 1], vf[u][j], vf[u][j + 1]);
           }
         }
+        float d = d0 + d1;
 #pragma unroll
         for (int o = 1; o < PL; o <<= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
         if (valid && pc == 0) s_dot[id] = d;
