@@ -249,10 +249,13 @@ class Problem:
         self.bwd()
 
 
-def time_steps(torch, fn, steps, warmup, barrier):
-    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events."""
+def time_steps(torch, fn, steps, warmup, barrier, finish=None):
+    """W untimed + exactly K timed steps, barrier + synchronize on both sides, CUDA events.
+    `finish` (optional) joins work `fn` enqueued on other streams back into the timed stream."""
     for _ in range(warmup):
         fn()
+    if finish:
+        finish()
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
@@ -260,6 +263,8 @@ def time_steps(torch, fn, steps, warmup, barrier):
     e0.record()
     for _ in range(steps):
         fn()
+    if finish:
+        finish()
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -283,10 +288,26 @@ def profile_kernels(prob, iters):
 
 
 def e2e_steps(torch, wis, prob, steps, warmup, barrier):
-    """Same op through the public Python API with HOST (pinned) buffers: H2D of the step's inputs and D2H of its
-    results inside the timed region."""
+    """The op over HOST (pinned) buffers through the package's host-buffer API (`HostPipeline`, the
+    msda_b200_host_pipeline_* entry points): every step copies its inputs H2D and its results D2H inside the timed
+    region; the pipeline overlaps the two copy directions with the kernels, image by image."""
     host_in = [t.detach().cpu().pin_memory() for t in (prob.value, prob.loc, prob.attn, prob.go)]
-    h2d = sum(t.numel() * t.element_size() for t in host_in)
+    pipe = wis.HostPipeline(prob.batch, prob.shapes, H, D, P, value_dtype=prob.value.dtype, chunk_images=2, slots=3)
+    res = pipe.empty_outputs()
+    secs = time_steps(torch, lambda: pipe.step(*host_in, **res), steps, warmup, barrier, finish=pipe.join)
+    h2d, d2h = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+    # spot-check: the host results equal the device-buffer results of the same inputs
+    prob.fwd()
+    torch.cuda.synchronize()
+    if not torch.equal(res["output"].view(prob.out.shape), prob.out.cpu()):
+        raise SystemExit("e2e: host-pipeline output differs from the device-buffer call")
+    pipe.close()
+    return secs, h2d, d2h
+
+
+def e2e_autograd_steps(torch, wis, prob, steps, warmup, barrier):
+    """Un-pipelined comparison: torch copies + `ms_deform_attn` + autograd backward on one stream."""
+    host_in = [t.detach().cpu().pin_memory() for t in (prob.value, prob.loc, prob.attn, prob.go)]
     host_out = None
     lsi = prob.x["level_start_index"]
 
@@ -294,7 +315,7 @@ def e2e_steps(torch, wis, prob, steps, warmup, barrier):
         nonlocal host_out
         v, lo, a, go = (t.to("cuda", non_blocking=True) for t in host_in)
         v.requires_grad_(True), lo.requires_grad_(True), a.requires_grad_(True)
-        out = wis.ms_deform_attn(v, SHAPES_C2, lsi, lo, a)
+        out = wis.ms_deform_attn(v, prob.shapes, lsi, lo, a)
         out.backward(go)
         res = (out.detach(), v.grad, lo.grad, a.grad)
         if host_out is None:
@@ -302,9 +323,7 @@ def e2e_steps(torch, wis, prob, steps, warmup, barrier):
         for h, t in zip(host_out, res):
             h.copy_(t, non_blocking=True)
 
-    secs = time_steps(torch, step, steps, warmup, barrier)
-    d2h = sum(t.numel() * t.element_size() for t in host_out)
-    return secs, h2d, d2h
+    return time_steps(torch, step, steps, warmup, barrier)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -377,7 +396,11 @@ def run_b200(args, rank, world, local_rank):
     e2e_secs = max_over_ranks(e2e_secs)
     e2e = {"value": world * B_PER_GPU * e2e_k / e2e_secs, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_k, "ms_per_step": e2e_secs / e2e_k * 1e3,
-           "api": "weed_instance_segmentation_b200.ms_deform_attn + autograd backward, pinned host buffers"}
+           "api": "weed_instance_segmentation_b200.HostPipeline.step (msda_b200_host_pipeline_step), pinned host "
+                  "buffers, 2 images per chunk, 3 staging slots"}
+    ag_secs = max_over_ranks(e2e_autograd_steps(torch, wis, prob, 3, 3, barrier))
+    e2e["unpipelined"] = {"value": world * B_PER_GPU * 3 / ag_secs, "ms_per_step": ag_secs / 3 * 1e3,
+                          "api": "torch copies + ms_deform_attn + autograd backward on one stream"}
 
     extras = {}
     if not args.no_extras and world == 1:

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 3
+#define MSDA_B200_ABI_VERSION 4
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -160,6 +160,37 @@ int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* x 
  */
 int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev, cols*/, int64_t rows, int32_t cols,
                          void* stream);
+
+/*
+ * Host-buffer pipeline: the op with every tensor in HOST memory (the boundary a caller without device
+ * buffers binds; bench.py's `e2e` leg).  The batch is cut into chunks of `chunk_images` images; each chunk
+ * is copied to a device staging slot, run through msda_b200_forward (+ msda_b200_backward) and its results
+ * copied back, on three streams (H2D, compute, D2H) over a ring of `slots` staging slots, so the two copy
+ * directions and the kernels overlap -- within a step and across consecutive steps.  All host pointers use
+ * the layouts of msda_b200_forward / msda_b200_backward; page-locked (pinned) memory is needed for the
+ * copies to overlap.  The pipeline owns its device staging memory (cudaMalloc at create, on the current
+ * device) and copies the descriptor's host arrays; `query_order` (device pointer or NULL) stays caller-owned.
+ *
+ *   create : desc->B is the batch of one step; with_backward = 0 builds a forward-only pipeline
+ *            (grad_out and the grad_* pointers of step are then ignored).
+ *   step   : enqueue one whole batch; returns without waiting.  Work starts after everything already
+ *            enqueued on `stream` (fork).  Host buffers must stay untouched until join + synchronise.
+ *   join   : make `stream` wait for everything enqueued so far (join) -- CUDA events recorded on `stream`
+ *            before the first step and after join bracket the device time of the steps in between.
+ *   sync   : block the host until everything enqueued so far has finished.
+ */
+typedef struct msda_b200_host_pipeline msda_b200_host_pipeline;
+
+int msda_b200_host_pipeline_create(const msda_b200_desc* desc, int32_t chunk_images, int32_t slots,
+                                   int32_t with_backward, const int32_t* query_order /*dev|NULL*/,
+                                   msda_b200_host_pipeline** pipeline);
+int msda_b200_host_pipeline_step(msda_b200_host_pipeline* pipeline, const void* value /*host*/,
+                                 const float* sampling_loc /*host*/, const void* attn_weight /*host*/,
+                                 const void* grad_output /*host*/, void* output /*host*/, void* grad_value /*host*/,
+                                 float* grad_sampling_loc /*host*/, void* grad_attn_weight /*host*/, void* stream);
+int msda_b200_host_pipeline_join(msda_b200_host_pipeline* pipeline, void* stream);
+int msda_b200_host_pipeline_sync(msda_b200_host_pipeline* pipeline);
+int msda_b200_host_pipeline_destroy(msda_b200_host_pipeline* pipeline);
 
 /*
  * Profiling aid for bench.py: when desc->flags has MSDA_B200_FLAG_PROFILE the library records

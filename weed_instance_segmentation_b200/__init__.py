@@ -12,9 +12,11 @@ from .functional import (  # noqa: F401
     query_order_2d,
 )
 from .fused import MSDeformAttnFusedFunction, ms_deform_attn_fused  # noqa: F401
+from .host import HostPipeline  # noqa: F401
 from .hf_patch import install, installed, is_installed, uninstall  # noqa: F401
 
 __all__ = [
+    "HostPipeline",
     "MSDAError",
     "MSDeformAttnFunction",
     "ms_deform_attn",

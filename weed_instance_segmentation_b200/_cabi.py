@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_LEVELS = 8
 F32, BF16 = 0, 1
 FLAG_PROFILE = 1
@@ -31,6 +31,11 @@ EXPORTS = (
     "msda_b200_add_layernorm_forward",
     "msda_b200_add_layernorm_backward",
     "msda_b200_column_sum",
+    "msda_b200_host_pipeline_create",
+    "msda_b200_host_pipeline_step",
+    "msda_b200_host_pipeline_join",
+    "msda_b200_host_pipeline_sync",
+    "msda_b200_host_pipeline_destroy",
     "msda_b200_profile_ms",
     "msda_b200_launch_count",
 )
@@ -94,6 +99,17 @@ def load() -> ctypes.CDLL:
                                                      ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_host_pipeline_create.restype = ctypes.c_int
+    lib.msda_b200_host_pipeline_create.argtypes = [dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp,
+                                                   ctypes.POINTER(vp)]
+    lib.msda_b200_host_pipeline_step.restype = ctypes.c_int
+    lib.msda_b200_host_pipeline_step.argtypes = [vp] * 10
+    lib.msda_b200_host_pipeline_join.restype = ctypes.c_int
+    lib.msda_b200_host_pipeline_join.argtypes = [vp, vp]
+    lib.msda_b200_host_pipeline_sync.restype = ctypes.c_int
+    lib.msda_b200_host_pipeline_sync.argtypes = [vp]
+    lib.msda_b200_host_pipeline_destroy.restype = ctypes.c_int
+    lib.msda_b200_host_pipeline_destroy.argtypes = [vp]
     lib.msda_b200_profile_ms.restype = ctypes.c_int
     lib.msda_b200_profile_ms.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
     lib.msda_b200_launch_count.restype = ctypes.c_int64

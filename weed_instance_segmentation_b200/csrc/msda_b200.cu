@@ -799,6 +799,8 @@ extern "C" {
 
 // shared with layer_epilogue.cu (not part of the public header)
 int msda_b200_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+// shared with host_pipeline.cu: the descriptor checks of forward / backward
+int msda_b200_internal_validate(const msda_b200_desc* desc) { return validate(desc); }
 
 int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
 
