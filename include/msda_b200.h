@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 4
+#define MSDA_B200_ABI_VERSION 5
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -160,6 +160,31 @@ int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* x 
  */
 int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev, cols*/, int64_t rows, int32_t cols,
                          void* stream);
+
+/*
+ * Batched bilinear point sampling -- the `sample_point` primitive of the loss / matcher path
+ * (transformers/models/mask2former/modeling_mask2former.py:245-274: grid_sample, bilinear, zeros padding,
+ * align_corners=False, coordinates normalised to [0,1] as (x, y)).  One call samples R rows of K points:
+ *   planes[r]          device pointer to a contiguous (h, w) plane of rows[r].dtype (MSDA_B200_F32 / _BF16)
+ *   rows[r].coord_row  which row of `coords` (C, K, 2) the plane is sampled at (planes may share a point set)
+ *   out                (R, K) float32
+ * Planes are read in place: no gather of matched masks, no padding, no upcast.  The backward adds
+ * grad_out[r, k] * bilinear weight into grad_planes[r] (float32 planes, accumulated with atomics -- the caller
+ * zero-fills them; NULL entries are skipped).  Coordinates carry no gradient (the reference samples them under
+ * no_grad, M2F:721-729).
+ */
+typedef struct msda_b200_ps_row {
+  int32_t h, w;       /* plane extent                              */
+  int32_t coord_row;  /* row of the coordinate table               */
+  int32_t dtype;      /* MSDA_B200_F32 or MSDA_B200_BF16           */
+} msda_b200_ps_row;
+
+int msda_b200_point_sample_forward(const void* const* planes /*dev, R*/, const msda_b200_ps_row* rows /*dev, R*/,
+                                   const float* coords /*dev, (C,K,2)*/, float* out /*dev, (R,K)*/, int64_t R,
+                                   int32_t K, void* stream);
+int msda_b200_point_sample_backward(float* const* grad_planes /*dev, R*/, const msda_b200_ps_row* rows /*dev, R*/,
+                                    const float* coords /*dev*/, const float* grad_out /*dev, (R,K)*/, int64_t R,
+                                    int32_t K, void* stream);
 
 /*
  * Host-buffer pipeline: the op with every tensor in HOST memory (the boundary a caller without device

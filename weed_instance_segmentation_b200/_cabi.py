@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_LEVELS = 8
 F32, BF16 = 0, 1
 FLAG_PROFILE = 1
@@ -31,6 +31,8 @@ EXPORTS = (
     "msda_b200_add_layernorm_forward",
     "msda_b200_add_layernorm_backward",
     "msda_b200_column_sum",
+    "msda_b200_point_sample_forward",
+    "msda_b200_point_sample_backward",
     "msda_b200_host_pipeline_create",
     "msda_b200_host_pipeline_step",
     "msda_b200_host_pipeline_join",
@@ -99,6 +101,10 @@ def load() -> ctypes.CDLL:
                                                      ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_point_sample_forward.restype = ctypes.c_int
+    lib.msda_b200_point_sample_forward.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_point_sample_backward.restype = ctypes.c_int
+    lib.msda_b200_point_sample_backward.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_host_pipeline_create.restype = ctypes.c_int
     lib.msda_b200_host_pipeline_create.argtypes = [dp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp,
                                                    ctypes.POINTER(vp)]

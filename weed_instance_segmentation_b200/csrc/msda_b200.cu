@@ -801,6 +801,8 @@ extern "C" {
 int msda_b200_internal_fail(int code, const char* msg) { return fail(code, "%s", msg); }
 // shared with host_pipeline.cu: the descriptor checks of forward / backward
 int msda_b200_internal_validate(const msda_b200_desc* desc) { return validate(desc); }
+// shared with point_sample.cu: kernels launched outside this file count too
+void msda_b200_internal_count_launch(void) { ++g_launches; }
 
 int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
 

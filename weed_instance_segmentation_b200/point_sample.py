@@ -1,0 +1,123 @@
+"""Batched bilinear point sampling over planes that stay where they are.
+
+The reference's ``sample_point`` (M2F:245-274) is ``grid_sample`` on a ``(R, 1, h, w)`` tensor, which forces the
+callers to gather / pad / upcast the masks into such a tensor first (M2F:455-474, :689-705). ``point_sample`` takes
+the original tensors and a per-row address instead::
+
+    out[r, k] = bilinear(sources[src_id[r]][plane_id[r]], coords[coord_row[r], k])        # (R, K) float32
+
+with ``grid_sample``'s conventions (bilinear, zeros padding, ``align_corners=False``, coordinates in [0, 1] as (x, y)).
+Gradients flow to the sources that require them (scatter with fp32 atomics); coordinates carry none.
+CUDA only: ``csrc/point_sample.cu`` through the C ABI, no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+
+class _Rows:
+    """Host-built address tables of one call (kept for the backward)."""
+
+    def __init__(self, sources: Sequence[torch.Tensor], src_id, plane_id, coord_row, device):
+        src_id = np.asarray(src_id, dtype=np.int64).reshape(-1)
+        plane_id = np.asarray(plane_id, dtype=np.int64).reshape(-1)
+        coord_row = np.asarray(coord_row, dtype=np.int64).reshape(-1)
+        if not (src_id.shape == plane_id.shape == coord_row.shape):
+            raise ValueError("point_sample: src_id, plane_id and coord_row must have one entry per row")
+        self.R = int(src_id.shape[0])
+        self.src_id, self.plane_id = src_id, plane_id
+        n = np.array([s.shape[0] for s in sources], dtype=np.int64)
+        self.h = np.array([s.shape[1] for s in sources], dtype=np.int64)
+        self.w = np.array([s.shape[2] for s in sources], dtype=np.int64)
+        if self.R:
+            if src_id.min() < 0 or src_id.max() >= len(sources):
+                raise ValueError("point_sample: src_id out of range")
+            if plane_id.min() < 0 or (plane_id >= n[src_id]).any():
+                raise ValueError("point_sample: plane_id out of range for its source")
+        base = np.array([s.data_ptr() for s in sources], dtype=np.int64)
+        item = np.array([s.element_size() for s in sources], dtype=np.int64)
+        code = np.array([_DTYPE_CODE[s.dtype] for s in sources], dtype=np.int64)
+        ptr = base[src_id] + plane_id * (self.h * self.w * item)[src_id]
+        rows = np.stack([self.h[src_id], self.w[src_id], coord_row, code[src_id]], axis=1).astype(np.int32)
+        self.device = device
+        self.ptr = torch.from_numpy(ptr).to(device, non_blocking=True)
+        self.rows = torch.from_numpy(np.ascontiguousarray(rows)).to(device, non_blocking=True)
+        self.max_coord_row = int(coord_row.max()) if self.R else -1
+
+    def grad_pointers(self, grads: Sequence[torch.Tensor | None]) -> torch.Tensor:
+        base = np.array([g.data_ptr() if g is not None else 0 for g in grads], dtype=np.int64)
+        live = base[self.src_id] != 0
+        ptr = np.where(live, base[self.src_id] + self.plane_id * (self.h * self.w * 4)[self.src_id], 0)
+        return torch.from_numpy(ptr).to(self.device, non_blocking=True)
+
+
+class PointSampleFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords, table, *sources):
+        lib = _cabi.load()
+        K = coords.shape[1]
+        out = torch.empty((table.R, K), dtype=torch.float32, device=coords.device)
+        with torch.cuda.device(coords.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _cabi.check(lib.msda_b200_point_sample_forward(table.ptr.data_ptr() if table.R else None,
+                                                           table.rows.data_ptr() if table.R else None,
+                                                           coords.data_ptr() if coords.numel() else None,
+                                                           out.data_ptr() if out.numel() else None, table.R, K, stream))
+        ctx.table = table
+        ctx.save_for_backward(coords)
+        ctx.src_meta = [(s.shape, s.dtype) for s in sources]
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        lib = _cabi.load()
+        (coords,) = ctx.saved_tensors
+        table = ctx.table
+        K = coords.shape[1]
+        needs = ctx.needs_input_grad[2:]
+        grads = [torch.zeros(shape, dtype=torch.float32, device=coords.device) if need else None
+                 for (shape, _), need in zip(ctx.src_meta, needs)]
+        if table.R and K and any(needs):
+            go = grad_out.float().contiguous()
+            gptr = table.grad_pointers(grads)
+            with torch.cuda.device(coords.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                _cabi.check(lib.msda_b200_point_sample_backward(gptr.data_ptr(), table.rows.data_ptr(), coords.data_ptr(),
+                                                                go.data_ptr(), table.R, K, stream))
+        outs = [g.to(dt) if g is not None else None for g, (_, dt) in zip(grads, ctx.src_meta)]
+        return (None, None, *outs)
+
+
+def point_sample(sources: Sequence[torch.Tensor], src_id, plane_id, coords: torch.Tensor, coord_row) -> torch.Tensor:
+    """Sample ``R`` planes at ``K`` points each; see the module docstring.
+
+    ``sources``: CUDA tensors ``(n_j, h_j, w_j)``, float32 or bfloat16 (non-contiguous ones are copied);
+    ``src_id`` / ``plane_id`` / ``coord_row``: host integer arrays of length ``R``;
+    ``coords``: ``(C, K, 2)`` CUDA float tensor of (x, y) in [0, 1]. Returns ``(R, K)`` float32.
+    """
+    if not isinstance(coords, torch.Tensor) or not coords.is_cuda:
+        raise RuntimeError("point_sample: tensors must live on a CUDA device (this package has no CPU fallback)")
+    if coords.dim() != 3 or coords.shape[-1] != 2:
+        raise ValueError(f"point_sample: coords must be (C, K, 2), got {tuple(coords.shape)}")
+    srcs = []
+    for s in sources:
+        if not s.is_cuda:
+            raise RuntimeError("point_sample: tensors must live on a CUDA device (this package has no CPU fallback)")
+        if s.dim() != 3:
+            raise ValueError(f"point_sample: every source must be (n, h, w), got {tuple(s.shape)}")
+        if s.dtype not in _DTYPE_CODE:
+            raise TypeError(f"point_sample: float32 or bfloat16 sources only, got {s.dtype}")
+        srcs.append(s if s.is_contiguous() else s.contiguous())
+    coords = coords.detach().float().contiguous()
+    table = _Rows(srcs, src_id, plane_id, coord_row, coords.device)
+    if table.max_coord_row >= coords.shape[0]:
+        raise ValueError("point_sample: coord_row out of range")
+    return PointSampleFunction.apply(coords, table, *srcs)
