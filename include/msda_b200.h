@@ -51,6 +51,7 @@ extern "C" {
 /* dtype codes */
 #define MSDA_B200_F32 0
 #define MSDA_B200_BF16 1
+#define MSDA_B200_U8 2 /* planes of msda_b200_point_sample_forward only (binary target masks stay 1 byte/pixel) */
 
 /* error codes */
 #define MSDA_B200_OK 0
@@ -165,7 +166,7 @@ int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev
  * Batched bilinear point sampling -- the `sample_point` primitive of the loss / matcher path
  * (transformers/models/mask2former/modeling_mask2former.py:245-274: grid_sample, bilinear, zeros padding,
  * align_corners=False, coordinates normalised to [0,1] as (x, y)).  One call samples R rows of K points:
- *   planes[r]          device pointer to a contiguous (h, w) plane of rows[r].dtype (MSDA_B200_F32 / _BF16)
+ *   planes[r]          device pointer to a contiguous (h, w) plane of rows[r].dtype (MSDA_B200_F32 / _BF16 / _U8)
  *   rows[r].coord_row  which row of `coords` (C, K, 2) the plane is sampled at (planes may share a point set)
  *   out                (R, K) float32
  * Planes are read in place: no gather of matched masks, no padding, no upcast.  The backward adds
@@ -176,7 +177,7 @@ int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev
 typedef struct msda_b200_ps_row {
   int32_t h, w;       /* plane extent                              */
   int32_t coord_row;  /* row of the coordinate table               */
-  int32_t dtype;      /* MSDA_B200_F32 or MSDA_B200_BF16           */
+  int32_t dtype;      /* MSDA_B200_F32, MSDA_B200_BF16 or MSDA_B200_U8 */
 } msda_b200_ps_row;
 
 int msda_b200_point_sample_forward(const void* const* planes /*dev, R*/, const msda_b200_ps_row* rows /*dev, R*/,

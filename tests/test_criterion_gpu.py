@@ -116,3 +116,20 @@ def test_criterion_full_size_matches_reference(ps):
         assert torch.allclose(got[k], want[k], rtol=1e-4, atol=1e-6), (k, float(got[k]), float(want[k]))
     for a, b in zip(gm_got, gm_want):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-3
+
+
+def test_uint8_and_bool_target_masks_give_the_same_losses(ps):
+    """Binary target masks may stay one byte per pixel (synth.collate_batch(mask_dtype=torch.uint8))."""
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+    loss, masks, classes, mask_labels, class_labels = make_problem(2, num_points=200)
+    mine = convert_criterion(loss.cuda())
+    masks, classes = [m.cuda() for m in masks], [c.cuda() for c in classes]
+    class_labels = [c.cuda() for c in class_labels]
+    outs = []
+    for dt in (torch.float32, torch.uint8, torch.bool):
+        labels = [m.to(dt).cuda() for m in mask_labels]
+        out, gm, _ = _run(mine, masks, classes, labels, class_labels, seed=5)
+        outs.append((out, gm))
+    for out, gm in outs[1:]:
+        for k in outs[0][0]:
+            assert torch.equal(out[k], outs[0][0][k]), k

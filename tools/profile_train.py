@@ -87,6 +87,10 @@ def main():
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         micro(batches[0])
         torch.cuda.synchronize()
+    for ev in prof.key_averages():
+        if ev.key.startswith("b200_loss::"):
+            print(json.dumps({"region": ev.key, "cpu_ms": ev.cpu_time_total / 1e3, "cuda_ms": ev.device_time_total / 1e3,
+                              "calls": ev.count}))
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=70))
     print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=15, max_name_column_width=70))
 

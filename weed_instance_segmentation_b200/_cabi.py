@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
 ABI_VERSION = 5
 MAX_LEVELS = 8
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 FLAG_PROFILE = 1
 FLAG_BF16_ATOMICS = 2
 FLAG_BWD_V1 = 4

@@ -29,6 +29,7 @@ import functools
 import numpy as np
 import torch
 import torch.nn.functional as F
+from torch.profiler import record_function
 
 
 def _host_int(values) -> np.ndarray:
@@ -56,7 +57,7 @@ def _criterion_forward(self, masks_queries_logits, class_queries_logits, mask_la
 
     with torch.autocast(device.type, enabled=False):
         # ---- 1. the reference's random draws, in its order (M2F:455 per image, then M2F:718 and :735 per layer)
-        with torch.no_grad():
+        with torch.no_grad(), record_function("b200_loss::random_points"):
             pts_match, pts_over, pts_rand = [], [], []
             for _ in range(L):
                 pts_match.extend(torch.rand(1, K_match, 2, device=device) for _ in range(B))
@@ -65,12 +66,13 @@ def _criterion_forward(self, masks_queries_logits, class_queries_logits, mask_la
                     pts_rand.append(torch.rand(M, k_rand, 2, device=device))
 
         preds = [m.reshape(B * Q, h, w) for m in layer_masks]                    # views: gradients reach the layers
-        targets = [t if t.dtype in (torch.float32, torch.bfloat16) else t.float() for t in mask_labels]
+        targets = [t if t.dtype in (torch.float32, torch.bfloat16, torch.uint8, torch.bool) else t.float()
+                   for t in mask_labels]                                             # binary masks may stay 1 byte/pixel
         targets = [t.reshape(-1, *t.shape[-2:]) for t in targets]
         sources = preds + targets
 
         # ---- 2. matcher costs of every (layer, image) at once (M2F:440-470)
-        with torch.no_grad():
+        with torch.no_grad(), record_function("b200_loss::matcher_costs"):
             lay, img = np.divmod(np.arange(L * B), B)
             p_src = np.repeat(lay, Q)
             p_plane = (np.repeat(img, Q) * Q + np.tile(np.arange(Q), L * B))
@@ -101,9 +103,10 @@ def _criterion_forward(self, masks_queries_logits, class_queries_logits, mask_la
             cost = torch.nan_to_num(cost.clamp(-1e10, 1e10), 0)
             cost_host = cost.cpu().numpy()                                      # the one synchronisation
         indices = []                                                            # [layer][image] -> (pred idx, target idx)
-        for li in range(L * B):
-            i = int(img[li])
-            indices.append(linear_sum_assignment(cost_host[li][:, : n_tgt[i]]))
+        with record_function("b200_loss::assignment"):
+            for li in range(L * B):
+                i = int(img[li])
+                indices.append(linear_sum_assignment(cost_host[li][:, : n_tgt[i]]))
 
         # ---- 3. matched rows of every layer, in the reference's order (M2F:707-716)
         img_of_pair = np.concatenate([np.full(n_match[i], i) for i in range(B)]) if M else np.zeros(0, np.int64)
@@ -117,7 +120,7 @@ def _criterion_forward(self, masks_queries_logits, class_queries_logits, mask_la
         row_ids = np.arange(L * M)
 
         # ---- 4. importance sampling of the loss points (M2F:646-687), all layers in one pass
-        with torch.no_grad():
+        with torch.no_grad(), record_function("b200_loss::importance_sampling"):
             coords_over = torch.cat(pts_over)                                                   # (L*M, k_over, 2)
             over = sampler(sources, lay_of_row, pred_plane.reshape(-1), coords_over, row_ids)     # (L*M, k_over)
             idx = torch.topk(-over.abs(), k=k_unc, dim=1)[1]

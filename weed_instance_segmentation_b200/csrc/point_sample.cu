@@ -42,6 +42,7 @@ __device__ __forceinline__ Corner corner_setup(float c, int n) {
 }
 
 __device__ __forceinline__ float load_plane(const void* plane, int dtype, long long idx) {
+  if (dtype == MSDA_B200_U8) return (float)__ldg(reinterpret_cast<const unsigned char*>(plane) + idx);
   return dtype == MSDA_B200_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(plane)[idx])
                                  : __ldg(reinterpret_cast<const float*>(plane) + idx);
 }

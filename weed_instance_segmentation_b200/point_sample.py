@@ -19,7 +19,7 @@ import torch
 
 from . import _cabi
 
-_DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+_DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.uint8: _cabi.U8, torch.bool: _cabi.U8}
 
 
 class _Rows:
@@ -99,7 +99,8 @@ class PointSampleFunction(torch.autograd.Function):
 def point_sample(sources: Sequence[torch.Tensor], src_id, plane_id, coords: torch.Tensor, coord_row) -> torch.Tensor:
     """Sample ``R`` planes at ``K`` points each; see the module docstring.
 
-    ``sources``: CUDA tensors ``(n_j, h_j, w_j)``, float32 or bfloat16 (non-contiguous ones are copied);
+    ``sources``: CUDA tensors ``(n_j, h_j, w_j)``, float32 / bfloat16, or uint8 / bool for binary masks that need no
+    gradient (non-contiguous ones are copied);
     ``src_id`` / ``plane_id`` / ``coord_row``: host integer arrays of length ``R``;
     ``coords``: ``(C, K, 2)`` CUDA float tensor of (x, y) in [0, 1]. Returns ``(R, K)`` float32.
     """
@@ -114,7 +115,7 @@ def point_sample(sources: Sequence[torch.Tensor], src_id, plane_id, coords: torc
         if s.dim() != 3:
             raise ValueError(f"point_sample: every source must be (n, h, w), got {tuple(s.shape)}")
         if s.dtype not in _DTYPE_CODE:
-            raise TypeError(f"point_sample: float32 or bfloat16 sources only, got {s.dtype}")
+            raise TypeError(f"point_sample: float32, bfloat16, uint8 or bool sources only, got {s.dtype}")
         srcs.append(s if s.is_contiguous() else s.contiguous())
     coords = coords.detach().float().contiguous()
     table = _Rows(srcs, src_id, plane_id, coord_row, coords.device)

@@ -148,8 +148,14 @@ def collate_batch(
     max_instances: int = 20,
     seed: int = 0,
     device="cpu",
+    mask_dtype: torch.dtype = torch.float32,
+    pin_memory: bool = False,
 ) -> dict:
     """A batch in the reference's ``collate_fn`` layout (dataset_utils.py:45-53).
+
+    ``mask_dtype=torch.uint8`` keeps the binary masks at one byte per pixel (a quarter of the host->device bytes;
+    the batched criterion samples them as they are, the stock criterion needs float32); ``pin_memory`` page-locks
+    ``pixel_values`` and the masks so that ``Trainer.prefetch`` copies them asynchronously.
 
     ``pixel_values`` (B,3,H,W) float32 stacked; ``mask_labels`` list of (N_i,H,W) float32 binary
     masks; ``class_labels`` list of (N_i,) int64; ``target_sizes`` list of (h,w);
@@ -180,14 +186,15 @@ def collate_batch(
             inst[height // 2, width // 2] = 1
             mapping.setdefault(1, 0)
             ids = [1]
-        mask_labels.append(torch.stack([(inst == k).float() for k in ids]).to(device))
+        masks = torch.stack([(inst == k) for k in ids]).to(mask_dtype)
+        mask_labels.append(masks.pin_memory() if pin_memory else masks.to(device))
         class_labels.append(torch.tensor([mapping[k] for k in ids], dtype=torch.int64, device=device))
         maps.append(inst)
         mappings.append({k: mapping[k] for k in ids})
         names.append(f"synthetic_{seed}_{i}.png")
         sizes.append((height, width))
     return {
-        "pixel_values": pixel_values.to(device),
+        "pixel_values": pixel_values.pin_memory() if pin_memory else pixel_values.to(device),
         "mask_labels": mask_labels,
         "class_labels": class_labels,
         "target_sizes": sizes,

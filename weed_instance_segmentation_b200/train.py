@@ -51,15 +51,19 @@ def build_model(backbone: str = "swin_t", num_labels: int = 3, seed: int = 0, **
     return Mask2FormerForUniversalSegmentation(cfg)
 
 
-def use_b200_path(model, mode: str = "modules") -> None:
+def use_b200_path(model, mode: str = "modules", criterion: bool = True) -> None:
     """Route the model's pixel-decoder MSDeformAttn through libmsda_b200.so.
 
     ``mode="function"`` rebinds the module-global function only (M2F:980); ``mode="modules"`` also
-    swaps the encoder layers for the mirrors in ``modules.py`` (drops the per-layer isfinite sync).
+    swaps the encoder layers for the mirrors in ``modules.py`` (drops the per-layer isfinite sync) and, with
+    ``criterion=True``, switches the loss / matcher to the batched path (``criterion.convert_criterion``).
     """
     hf_patch.install()
     if mode == "modules":
         modules.convert_pixel_decoder(model)
+        if criterion and hasattr(model, "criterion"):
+            from .criterion import convert_criterion
+            convert_criterion(model)
 
 
 def install_distributed_num_masks() -> None:
@@ -104,12 +108,40 @@ class Trainer:
         self.micro = 0
         self.loss_sum = torch.zeros((), device=self.device)
         self.loss_count = 0
+        self._copy_stream = None
+
+    def prefetch(self, batch: dict) -> dict:
+        """Start copying a host batch to the device on a side stream; pass the result to ``step``.
+
+        With page-locked host tensors (``synth.collate_batch(pin_memory=True)``, or a ``DataLoader`` with
+        ``pin_memory=True``) the copy runs under the previous micro-batch's kernels; pageable tensors still work
+        but block the host while they are staged (what the reference's ``.to(device)`` at train.py:193-195 does).
+        """
+        if self.device.type != "cuda":
+            return batch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            out = {
+                "pixel_values": batch["pixel_values"].to(self.device, non_blocking=True),
+                "mask_labels": [m.to(self.device, non_blocking=True) for m in batch["mask_labels"]],
+                "class_labels": [c.to(self.device, non_blocking=True) for c in batch["class_labels"]],
+            }
+            ready = torch.cuda.Event()
+            ready.record()
+        out["_ready"] = ready
+        return out
 
     def step(self, batch: dict) -> torch.Tensor:
         """One micro-batch: train.py:192-202. Returns the (undivided) loss tensor, still on device."""
         pixel_values = batch["pixel_values"].to(self.device, non_blocking=True)
         mask_labels = [m.to(self.device, non_blocking=True) for m in batch["mask_labels"]]
         class_labels = [c.to(self.device, non_blocking=True) for c in batch["class_labels"]]
+        if batch.get("_ready") is not None:  # came through prefetch(): order after the side-stream copies
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(batch["_ready"])
+            for t in (pixel_values, *mask_labels, *class_labels):
+                t.record_stream(cur)
         last = (self.micro + 1) % self.grad_accum == 0
         sync_ctx = contextlib.nullcontext() if (last or self.net is self.model) else self.net.no_sync()
         amp = (torch.autocast(self.device.type, dtype=self.amp_dtype) if self.amp_dtype is not None
@@ -135,12 +167,22 @@ class Trainer:
         return v
 
 
-def throughput(trainer: Trainer, batches: list, steps: int, warmup: int) -> float:
-    """Seconds for ``steps`` micro-batches after ``warmup`` (device-timed on CUDA, barrier on both sides)."""
+def throughput(trainer: Trainer, batches: list, steps: int, warmup: int, prefetch: bool = False) -> float:
+    """Seconds for ``steps`` micro-batches after ``warmup`` (device-timed on CUDA, barrier on both sides).
+    Every micro-batch starts from HOST tensors; ``prefetch`` copies batch i+1 while batch i computes."""
     cuda = trainer.device.type == "cuda"
     multi = dist.is_available() and dist.is_initialized()
-    for i in range(warmup):
-        trainer.step(batches[i % len(batches)])
+    if prefetch and cuda:
+        def run(n):
+            nxt = trainer.prefetch(batches[0])
+            for i in range(n):
+                cur, nxt = nxt, (trainer.prefetch(batches[(i + 1) % len(batches)]) if i + 1 < n else None)
+                trainer.step(cur)
+    else:
+        def run(n):
+            for i in range(n):
+                trainer.step(batches[i % len(batches)])
+    run(warmup)
     if cuda:
         torch.cuda.synchronize()
     if multi:
@@ -150,8 +192,7 @@ def throughput(trainer: Trainer, batches: list, steps: int, warmup: int) -> floa
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     t0 = time.perf_counter()
-    for i in range(steps):
-        trainer.step(batches[i % len(batches)])
+    run(steps)
     if cuda:
         e1.record()
         torch.cuda.synchronize()
@@ -216,9 +257,13 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per micro-batch")
     ap.add_argument("--classes", type=int, default=3)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--impl", choices=["b200", "b200-function", "reference"], default="b200")
+    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--impl", choices=["b200", "b200-stock-loss", "b200-function", "reference"], default="b200")
     ap.add_argument("--amp", choices=["none", "bf16"], default="none")
+    ap.add_argument("--input", choices=["auto", "reference", "b200"], default="auto",
+                    help="host batch layout: reference = pageable float32 masks copied inside the step; b200 = pinned "
+                         "uint8 masks prefetched on a side stream (needs the batched criterion); auto = b200 for "
+                         "--impl b200, reference otherwise")
     ap.add_argument("--infer", action="store_true",
                     help="inference replicas instead of training (the reference's run_inference call shape, "
                          "/root/reference/models/mask2former/inference.py:25-30): eval(), no_grad, no collective")
@@ -236,6 +281,8 @@ def main(argv=None):
     model = build_model(args.backbone, num_labels=args.classes, seed=0)
     if args.impl == "b200":
         use_b200_path(model, "modules")
+    elif args.impl == "b200-stock-loss":
+        use_b200_path(model, "modules", criterion=False)
     elif args.impl == "b200-function":
         use_b200_path(model, "function")
     if args.infer:
@@ -253,9 +300,16 @@ def main(argv=None):
             dist.destroy_process_group()
         return
     trainer = Trainer(model, device, amp_dtype=torch.bfloat16 if args.amp == "bf16" else None)
-    batches = [synth.collate_batch(args.batch, args.height, args.width, num_classes=args.classes, seed=1000 * rank + i)
+    # Input path: the reference hands pageable float32 masks to `.to(device)` inside the step (train.py:193-195, a
+    # DataLoader without pin_memory); the full B200 path keeps the binary masks at one byte per pixel in page-locked
+    # memory and copies batch i+1 under batch i (`--input reference` forces the reference's layout for either arm).
+    native_input = args.input == "b200" or (args.input == "auto" and args.impl == "b200")
+    cuda = device.type == "cuda"
+    batches = [synth.collate_batch(args.batch, args.height, args.width, num_classes=args.classes, seed=1000 * rank + i,
+                                   mask_dtype=torch.uint8 if native_input else torch.float32,
+                                   pin_memory=native_input and cuda)
                for i in range(2)]
-    secs = throughput(trainer, batches, args.steps, args.warmup)
+    secs = throughput(trainer, batches, args.steps, args.warmup, prefetch=native_input)
     loss = trainer.mean_loss()
     if rank == 0:
         print(json.dumps({
@@ -265,7 +319,9 @@ def main(argv=None):
             "dtype": "bf16 autocast" if args.amp == "bf16" else "f32",
             "config": {"workload": f"Mask2Former {args.backbone} fine-tune step, {args.height}x{args.width}, "
                                    f"{args.classes} classes, batch {args.batch}/GPU, AdamW lr {LEARNING_RATE}, "
-                                   f"grad accumulation {GRADIENT_ACCUMULATION}"},
+                                   f"grad accumulation {GRADIENT_ACCUMULATION}",
+                       "input": ("pinned uint8 masks, prefetched" if native_input
+                                 else "pageable float32 masks copied inside the step (as the reference)")},
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
