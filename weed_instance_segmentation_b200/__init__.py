@@ -12,11 +12,17 @@ from .functional import (  # noqa: F401
     query_order_2d,
 )
 from .fused import MSDeformAttnFusedFunction, ms_deform_attn_fused  # noqa: F401
+from . import criterion  # noqa: F401
+from .criterion import convert_criterion, restore_criterion  # noqa: F401
 from .host import HostPipeline  # noqa: F401
+from .point_sample import point_sample  # noqa: F401
 from .hf_patch import install, installed, is_installed, uninstall  # noqa: F401
 
 __all__ = [
     "HostPipeline",
+    "convert_criterion",
+    "restore_criterion",
+    "point_sample",
     "MSDAError",
     "MSDeformAttnFunction",
     "ms_deform_attn",
