@@ -32,7 +32,8 @@ def models():
                 p.add_(0.1 + 0.3 * torch.rand(p.shape, generator=g, device="cuda"))
     fn = copy.deepcopy(ref)
     mod = copy.deepcopy(ref)
-    return ref, fn, mod
+    full = copy.deepcopy(ref)
+    return ref, fn, mod, full
 
 
 def _rel(a, b):
@@ -53,11 +54,14 @@ def _forward(model, batch, patched):
 @pytest.mark.parametrize("size", [(128, 160), (97, 130)])
 def test_logits_loss_and_grads_match_reference(models, size):
     from weed_instance_segmentation_b200 import _cabi, modules, synth
-    ref, fn, mod = models
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+    ref, fn, mod, full = models
     modules.convert_pixel_decoder(mod)
+    modules.convert_pixel_decoder(full)
+    convert_criterion(full)  # + batched loss / matcher: same random points, so the loss is comparable to 1e-4 as well
     batch = synth.collate_batch(2, size[0], size[1], num_classes=3, max_instances=4, seed=3, device="cuda")
     outs = {}
-    for name, model, patched in (("ref", ref, False), ("fn", fn, True), ("mod", mod, True)):
+    for name, model, patched in (("ref", ref, False), ("fn", fn, True), ("mod", mod, True), ("full", full, True)):
         model.train()
         model.zero_grad(set_to_none=True)
         _cabi.launch_count(reset=True)
@@ -66,7 +70,8 @@ def test_logits_loss_and_grads_match_reference(models, size):
         outs[name] = (out, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
                       _cabi.launch_count())
     assert outs["ref"][2] == 0 and outs["fn"][2] >= 6 * 2 and outs["mod"][2] >= 6 * 2  # 6 layers fwd + bwd kernels
-    for name in ("fn", "mod"):
+    assert outs["full"][2] >= 6 * 2 + 4  # + three sampling launches and their backward
+    for name in ("fn", "mod", "full"):
         o, g, _ = outs[name]
         r, rg, _ = outs["ref"]
         # the op agrees with the reference to ~1e-6 per call (test_msda_gpu); six encoder layers, LayerNorms and
@@ -86,7 +91,7 @@ def test_instance_masks_unchanged(models):
     from transformers import Mask2FormerImageProcessor
     import weed_instance_segmentation_b200 as wis
     from weed_instance_segmentation_b200 import synth
-    ref, fn, _ = models
+    ref, fn, _, _ = models
     proc = Mask2FormerImageProcessor()
     ious = []
     for seed in range(3):
@@ -115,7 +120,7 @@ def test_instance_masks_unchanged(models):
 def test_bf16_autocast_forward_close(models):
     from weed_instance_segmentation_b200 import synth
     import weed_instance_segmentation_b200 as wis
-    ref, fn, _ = models
+    ref, fn, _, _ = models
     batch = synth.collate_batch(2, 128, 160, num_classes=3, max_instances=4, seed=5, device="cuda")
     ref.eval(), fn.eval()
     with torch.no_grad():
