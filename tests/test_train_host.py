@@ -106,3 +106,34 @@ def test_modules_keep_state_dict_keys():
     assert modules.convert_pixel_decoder(m) == 0  # idempotent
     with pytest.raises(ValueError):
         modules.MSDeformAttn(250, 8, 3, 4)
+
+
+def test_batched_criterion_in_the_training_step_matches_stock_loss():
+    """Trainer.step with the converted criterion (grid_sample sampler injected: the CUDA sampler has no CPU path)
+    gives the stock criterion's loss and gradients for the same generator state, with uint8 masks as well."""
+    import copy
+
+    from test_criterion_host import grid_sample_sampler
+    from weed_instance_segmentation_b200 import synth, train
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+
+    torch.set_num_threads(4)
+    stock = build()
+    mine = copy.deepcopy(stock)
+    convert_criterion(mine, sampler=grid_sample_sampler)
+    b_f32 = synth.collate_batch(2, 64, 96, num_classes=3, max_instances=3, seed=4)
+    b_u8 = synth.collate_batch(2, 64, 96, num_classes=3, max_instances=3, seed=4, mask_dtype=torch.uint8)
+    assert all(torch.equal(a, b.float()) for a, b in zip(b_f32["mask_labels"], b_u8["mask_labels"]))
+    results = []
+    for model, batch in ((stock, b_f32), (mine, b_f32), (mine, b_u8)):
+        model.zero_grad(set_to_none=True)
+        tr = train.Trainer(model, "cpu", ddp=False)
+        torch.manual_seed(77)
+        loss = tr.step(tr.prefetch(batch))  # prefetch is the identity without a CUDA device
+        grads = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+        results.append((float(loss), grads.clone()))
+    for loss, grads in results[1:]:
+        assert abs(loss - results[0][0]) <= 1e-5 * abs(results[0][0])
+        scale = results[0][1].abs().max()
+        assert (grads - results[0][1]).abs().max() <= 2e-4 * scale
+    assert results[1][0] == results[2][0] and torch.equal(results[1][1], results[2][1])  # mask dtype is immaterial
