@@ -94,3 +94,14 @@ def test_default_sampler_refuses_cpu_tensors():
     mine = convert_criterion(loss)
     with pytest.raises(RuntimeError, match="CUDA"):
         mine(masks[0], classes[0], mask_labels, class_labels, None)
+
+
+def test_converted_loss_survives_pickle_and_deepcopy():
+    import pickle
+
+    from weed_instance_segmentation_b200 import criterion
+    loss, *_ = make_problem(0)
+    mine = criterion.convert_criterion(loss)
+    again = pickle.loads(pickle.dumps(mine))
+    assert type(again) is criterion.B200Mask2FormerLoss and type(copy.deepcopy(mine)) is type(mine)
+    assert torch.equal(again.empty_weight, mine.empty_weight)

@@ -176,8 +176,16 @@ def loss_class():
 
     return type("B200Mask2FormerLoss", (Mask2FormerLoss,), {
         "forward": _criterion_forward, "_b200_sampler": staticmethod(default_sampler), "last_indices": None,
-        "__doc__": _criterion_forward.__doc__ or __doc__,
+        "__doc__": __doc__, "__module__": __name__, "__qualname__": "B200Mask2FormerLoss",
     })
+
+
+def __getattr__(name):
+    # `criterion.B200Mask2FormerLoss` resolves lazily (transformers is imported on first use), which also lets
+    # pickle / copy find the class of a converted module by name.
+    if name == "B200Mask2FormerLoss":
+        return loss_class()
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 def convert_criterion(model_or_loss, sampler=None):
