@@ -18,10 +18,11 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ps():
-    from weed_instance_segmentation_b200 import _cabi, build, point_sample
+    from weed_instance_segmentation_b200 import _cabi, build
+    from weed_instance_segmentation_b200.point_sample import point_sample
     build.build()
     _cabi.load()
-    return point_sample.point_sample
+    return point_sample
 
 
 def _reference_rows(sources, src_id, plane_id, coords, coord_row):
