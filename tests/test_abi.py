@@ -79,3 +79,20 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "msda_oracle" not in text, f
+
+
+def test_new_entry_points_validate_before_touching_the_device(lib):
+    """Host pipeline and point sampling: argument errors are reported without a GPU; empty work succeeds."""
+    from weed_instance_segmentation_b200 import _cabi
+    handle = ctypes.c_void_p()
+    d, keep = _cabi.make_desc(2, 9, 9, 1, 32, 1, 1, _cabi.F32, _cabi.F32, [(3, 3)], [0])
+    assert lib.msda_b200_host_pipeline_create(ctypes.byref(d), 1, 1, 1, None, ctypes.byref(handle)) == 1  # slots < 2
+    assert b"slots" in lib.msda_b200_last_error() and not handle.value
+    bad, keep2 = _cabi.make_desc(2, 9, 9, 1, 24, 1, 1, _cabi.F32, _cabi.F32, [(3, 3)], [0])
+    assert lib.msda_b200_host_pipeline_create(ctypes.byref(bad), 1, 2, 1, None, ctypes.byref(handle)) == 2
+    assert lib.msda_b200_host_pipeline_step(None, *([None] * 9)) == 1
+    assert lib.msda_b200_host_pipeline_destroy(None) == 0
+    assert lib.msda_b200_point_sample_forward(None, None, None, None, 0, 128, None) == 0   # no rows
+    assert lib.msda_b200_point_sample_forward(None, None, None, None, 4, 128, None) == 1   # NULL tables
+    assert lib.msda_b200_point_sample_backward(None, None, None, None, -1, 128, None) == 1
+    assert ctypes.sizeof(ctypes.c_int32) * 4 == 16  # msda_b200_ps_row: four int32 (h, w, coord_row, dtype)
