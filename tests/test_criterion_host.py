@@ -105,3 +105,50 @@ def test_converted_loss_survives_pickle_and_deepcopy():
     again = pickle.loads(pickle.dumps(mine))
     assert type(again) is criterion.B200Mask2FormerLoss and type(copy.deepcopy(mine)) is type(mine)
     assert torch.equal(again.empty_weight, mine.empty_weight)
+
+
+def _compare(loss, masks, classes, mask_labels, class_labels, seed=5):
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+    want, gm_want, gc_want = run(loss, masks, classes, mask_labels, class_labels, seed=seed)
+    mine = convert_criterion(copy.deepcopy(loss), sampler=grid_sample_sampler)
+    got, gm_got, gc_got = run(mine, masks, classes, mask_labels, class_labels, seed=seed)
+    assert list(got) == list(want)
+    for k in want:
+        assert torch.allclose(got[k], want[k], rtol=1e-5, atol=1e-6), (k, float(got[k]), float(want[k]))
+    for a, b in zip(gm_got + gc_got, gm_want + gc_want):
+        a = torch.zeros_like(b) if a is None else a  # the injected sampler returns a constant for zero rows
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7), float((a - b).abs().max())
+
+
+def test_single_layer_single_image():
+    """No auxiliary predictions (the inference-time loss call shape) and a batch of one."""
+    loss, masks, classes, mask_labels, class_labels = make_problem(4, B=1, L=1, n_tgt=(3,))
+    _compare(loss, masks, classes, mask_labels, class_labels)
+
+
+def test_all_points_by_importance_and_no_oversampling():
+    """importance_sample_ratio = 1 (no uniformly random tail: the reference then skips one torch.rand per layer) and
+    oversample_ratio = 1 (top-k over exactly num_points candidates)."""
+    loss, masks, classes, mask_labels, class_labels = make_problem(5, L=2)
+    loss.importance_sample_ratio = 1.0
+    _compare(loss, masks, classes, mask_labels, class_labels)
+    loss.importance_sample_ratio = 0.75
+    loss.oversample_ratio = 1.0
+    _compare(loss, masks, classes, mask_labels, class_labels)
+
+
+def test_non_default_cost_weights_change_the_assignment_consistently():
+    loss, masks, classes, mask_labels, class_labels = make_problem(6, L=2, n_tgt=(6, 6, 6))
+    loss.matcher.cost_class, loss.matcher.cost_mask, loss.matcher.cost_dice = 5.0, 0.5, 2.0
+    _compare(loss, masks, classes, mask_labels, class_labels)
+
+
+def test_batch_without_any_target_matches_reference():
+    """No instance in the whole batch: the mask losses are exactly zero and only the "no object" class loss remains."""
+    loss, masks, classes, mask_labels, class_labels = make_problem(7, L=2, n_tgt=(0, 0, 0))
+    _compare(loss, masks, classes, mask_labels, class_labels)
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+    mine = convert_criterion(copy.deepcopy(loss), sampler=grid_sample_sampler)
+    out, gm, gc = run(mine, masks, classes, mask_labels, class_labels, seed=1)
+    assert out["loss_mask"].item() == 0.0 and out["loss_dice"].item() == 0.0 and out["loss_cross_entropy"].item() > 0
+    assert all(g is None or g.abs().max().item() == 0.0 for g in gm) and all(g.abs().max().item() > 0 for g in gc)
