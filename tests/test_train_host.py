@@ -16,13 +16,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, batched_loss=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from weed_instance_segmentation_b200 import synth, train
         model = build()
+        if batched_loss:  # the batched criterion's host logic under DDP (grid_sample stands in for the CUDA sampler)
+            import sys
+            sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+            from test_criterion_host import grid_sample_sampler
+            from weed_instance_segmentation_b200.criterion import convert_criterion
+            convert_criterion(model, sampler=grid_sample_sampler)
         tr = train.Trainer(model, "cpu")
         assert isinstance(tr.net, torch.nn.parallel.DistributedDataParallel)
         # num_masks is averaged over the group (what accelerate.reduce does at M2F:787-793)
@@ -55,12 +61,13 @@ def build():
     return train.build_model("swin_tiny_test", num_labels=3, seed=0, **TINY)
 
 
-def test_ddp_step_world2_gloo():
+@pytest.mark.parametrize("batched_loss", [False, True], ids=["stock-loss", "batched-loss"])
+def test_ddp_step_world2_gloo(batched_loss):
     pytest.importorskip("transformers")
     world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), out, batched_loss), nprocs=world, join=True)
         assert len(out) == world
 
 
