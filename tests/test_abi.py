@@ -38,9 +38,10 @@ def test_abi_version_and_error_string(lib):
 
 def test_desc_layout_matches_header():
     from weed_instance_segmentation_b200 import _cabi
-    # 10 x int32 then two pointers: 40 bytes + 16 on LP64
-    assert ctypes.sizeof(_cabi.Desc) == 10 * 4 + 2 * ctypes.sizeof(ctypes.c_void_p)
+    # 10 x int32, two host pointers, the tile-schedule pointer, 4 x int32: 40 + 16 + 8 + 16 bytes on LP64
+    assert ctypes.sizeof(_cabi.Desc) == 10 * 4 + 3 * ctypes.sizeof(ctypes.c_void_p) + 4 * 4
     assert _cabi.Desc.spatial_shapes_hw.offset == 40
+    assert _cabi.Desc.tile_start.offset == 56 and _cabi.Desc.num_tiles.offset == 64 and _cabi.Desc.tile_cols.offset == 76
 
 
 def test_validation_without_gpu(lib):

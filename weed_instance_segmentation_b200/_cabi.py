@@ -11,12 +11,13 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_LEVELS = 8
 F32, BF16, U8 = 0, 1, 2
 FLAG_PROFILE = 1
 FLAG_BF16_ATOMICS = 2
 FLAG_BWD_V1 = 4
+FLAG_NO_WINDOW = 8
 PROF_FWD, PROF_BWD_ZERO, PROF_BWD_MAIN, PROF_BWD_CONVERT = 0, 1, 2, 3
 
 # every symbol include/msda_b200.h declares
@@ -52,6 +53,8 @@ class Desc(ctypes.Structure):
         ("value_dtype", ctypes.c_int32), ("attn_dtype", ctypes.c_int32), ("flags", ctypes.c_uint32),
         ("spatial_shapes_hw", ctypes.POINTER(ctypes.c_int32)),
         ("level_start_index", ctypes.POINTER(ctypes.c_int64)),
+        ("tile_start", ctypes.c_void_p), ("num_tiles", ctypes.c_int32), ("max_tile", ctypes.c_int32),
+        ("tile_rows", ctypes.c_int32), ("tile_cols", ctypes.c_int32),
     ]
 
 
@@ -135,24 +138,33 @@ def check(rc: int) -> None:
 _desc_cache: dict = {}
 
 
-def make_desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, shapes_hw, level_start, flags=0):
+def make_desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, shapes_hw, level_start, flags=0, schedule=None):
     """Build a ``Desc`` plus the host arrays it points to (keep the returned tuple alive).
 
     Descriptors are immutable once built and the library only reads them during the call, so identical
-    problems share one cached instance (saves ~9 us of ctypes marshalling per call).
+    problems share one cached instance (saves ~9 us of ctypes marshalling per call). ``schedule`` is a
+    ``functional.Schedule`` (device tile table) or None.
     """
     key = (B, S, Q, H, D, L, P, value_dtype, attn_dtype, flags, tuple(tuple(hw) for hw in shapes_hw), tuple(level_start))
     hit = _desc_cache.get(key)
     if hit is not None:
         d, keep = hit
-        return Desc.from_buffer_copy(d), keep  # a private copy: callers may tweak fields (tests do)
-    shp = (ctypes.c_int32 * (2 * L))(*[int(v) for hw in shapes_hw for v in hw])
-    lsi = (ctypes.c_int64 * L)(*[int(v) for v in level_start])
-    d = Desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, flags, shp, lsi)
-    if len(_desc_cache) > 256:
-        _desc_cache.clear()
-    _desc_cache[key] = (d, (shp, lsi))
-    return Desc.from_buffer_copy(d), (shp, lsi)
+        d = Desc.from_buffer_copy(d)  # a private copy: callers may tweak fields (tests do)
+    else:
+        shp = (ctypes.c_int32 * (2 * L))(*[int(v) for hw in shapes_hw for v in hw])
+        lsi = (ctypes.c_int64 * L)(*[int(v) for v in level_start])
+        d0 = Desc(B, S, Q, H, D, L, P, value_dtype, attn_dtype, flags, shp, lsi, None, 0, 0, 0, 0)
+        if len(_desc_cache) > 256:
+            _desc_cache.clear()
+        keep = (shp, lsi)
+        _desc_cache[key] = (d0, keep)
+        d = Desc.from_buffer_copy(d0)
+    if schedule is not None:
+        d.tile_start = schedule.tile_start.data_ptr()
+        d.num_tiles = schedule.num_tiles
+        d.max_tile = schedule.max_tile
+        d.tile_rows, d.tile_cols = schedule.tile
+    return d, keep
 
 
 def profile_ms(which: int) -> float:

@@ -23,163 +23,19 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
 #include "msda_b200.h"
 
+// msda_win.cu: window-staged (TMA) kernels for the pixel decoder's geometry
+extern "C" int msda_b200_internal_win_applicable(const msda_b200_desc* desc, const void* query_order);
+extern "C" int msda_b200_internal_win_forward(const msda_b200_desc* desc, const void* kparams, void* stream);
+
 namespace {
 
-constexpr int kMaxL = MSDA_B200_MAX_LEVELS;
-
-struct Level {
-  int H, W;
-  int start;  // first row of this level in S
-  int dx16;   // +1 pixel in x, in 16-byte units of the value tensor (0 if W == 1)
-  int dy16;   // +1 pixel in y, in 16-byte units (0 if H == 1)
-};
-
-struct KParams {
-  const void* value;
-  const float* loc;
-  const void* attn;
-  void* out;             // forward
-  const void* grad_out;  // backward
-  void* grad_value_acc;  // backward: fp32 accumulator (grad_value itself for fp32) or bf16 grad_value
-  float* grad_loc;
-  void* grad_attn;
-  const int* q_order;
-  // fused prologue (M2F:952-971): raw sampling offsets and attention logits instead of loc / attn
-  const void* offsets;   // (B,Q,H,L,P,2), dtype AT
-  const void* logits;    // (B,Q,H,L*P),   dtype AT
-  const float* ref;      // (B,Q,L,2) reference points
-  float* attn_out;       // optional (B,Q,H,L,P) softmax output
-  void* grad_offsets;    // backward, dtype AT
-  void* grad_logits;     // backward, dtype AT
-  int B, S, Q, H, L, P, LP;
-  int num_tiles;
-  long long batch_stride16;  // S*H*D*sizeof(T)/16
-  Level lv[kMaxL];
-};
-
-// ---------------------------------------------------------------------------------------------
-// Sample descriptor maths (shared by forward and backward).
-// ---------------------------------------------------------------------------------------------
-struct Axis {
-  float s0, s1;  // weights of the two loaded slots (base, base+1)
-  float g0, g1;  // d(s0)/d(pixel coord), d(s1)/d(pixel coord)
-  int base;      // clamped index of slot 0
-  bool ok;
-};
-
-// coord: normalised location in [0,1] (may lie outside); n: level extent along this axis.
-// Follows M2F:807 (grid = 2*loc - 1) and ATen grid_sampler_unnormalize(align_corners=False):
-//   pix = ((grid + 1) * n - 1) / 2, evaluated in that order without FMA contraction.
-__device__ __forceinline__ Axis axis_setup(float coord, int n) {
-  Axis a;
-  const float g = __fadd_rn(__fmul_rn(2.f, coord), -1.f);
-  const float pix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)n), -1.f), 0.5f);
-  a.ok = (pix > -2.f) && (pix < (float)(n + 1));  // false for NaN as well
-  const float fl = floorf(pix);
-  const int i0 = __float2int_rd(pix);  // saturating; NaN -> 0
-  const float l = pix - fl;
-  const bool v0 = (i0 >= 0) && (i0 < n);
-  const bool v1 = (i0 + 1 >= 0) && (i0 + 1 < n);
-  const float w0 = v0 ? 1.f - l : 0.f, w1 = v1 ? l : 0.f;
-  const float d0 = v0 ? -1.f : 0.f, d1 = v1 ? 1.f : 0.f;
-  const int ib = min(max(i0, 0), max(n - 2, 0));
-  const int shift = i0 - ib;
-  a.base = ib;
-  a.s0 = (shift == 0) ? w0 : ((shift == -1) ? w1 : 0.f);
-  a.g0 = (shift == 0) ? d0 : ((shift == -1) ? d1 : 0.f);
-  a.s1 = (shift == 0) ? w1 : ((shift == 1) ? w0 : 0.f);
-  a.g1 = (shift == 0) ? d1 : ((shift == 1) ? d0 : 0.f);
-  if (!a.ok) a.s0 = a.s1 = a.g0 = a.g1 = 0.f;  // NaN / far outside: contributes exactly zero (0 * NaN would not)
-  return a;
-}
-
-template <typename T>
-__device__ __forceinline__ float to_float(T v);
-template <>
-__device__ __forceinline__ float to_float<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-template <typename T>
-__device__ __forceinline__ T from_float(float v);
-template <>
-__device__ __forceinline__ float from_float<float>(float v) { return v; }
-template <>
-__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
-// 16 bytes of T -> VEC floats
-template <typename T>
-struct Vec16;
-template <>
-struct Vec16<float> {
-  static constexpr int N = 4;
-  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[4]) {
-    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
-    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
-  }
-  static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
-    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-  }
-};
-template <>
-struct Vec16<__nv_bfloat16> {
-  static constexpr int N = 8;
-  static __device__ __forceinline__ void unpack(const uint4& v, float (&f)[8]) {
-    // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked.
-    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
-    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
-    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
-    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
-  }
-  static __device__ __forceinline__ unsigned pack2(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<unsigned*>(&h);
-  }
-  static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
-    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-  }
-};
-
-__device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
-
-// Packed fp32 FMA (sm_100a FFMA2): (a0, a1) += w * (f0, f1) and (a0, a1) += (g0, g1) * (f0, f1), each element rounded
-// exactly like fmaf. One instruction for two FMAs: the kernels here are bound by instruction issue, not by the FMA pipe.
-__device__ __forceinline__ void fma2_scalar(float& a0, float& a1, float w, float f0, float f1) {
-  asm("{ .reg .b64 ra, rw, rf;\n\t"
-      "mov.b64 ra, {%0, %1};\n\t"
-      "mov.b64 rw, {%2, %2};\n\t"
-      "mov.b64 rf, {%3, %4};\n\t"
-      "fma.rn.f32x2 ra, rw, rf, ra;\n\t"
-      "mov.b64 {%0, %1}, ra; }"
-      : "+f"(a0), "+f"(a1)
-      : "f"(w), "f"(f0), "f"(f1));
-}
-__device__ __forceinline__ void fma2_pair(float& a0, float& a1, float g0, float g1, float f0, float f1) {
-  asm("{ .reg .b64 ra, rg, rf;\n\t"
-      "mov.b64 ra, {%0, %1};\n\t"
-      "mov.b64 rg, {%2, %3};\n\t"
-      "mov.b64 rf, {%4, %5};\n\t"
-      "fma.rn.f32x2 ra, rg, rf, ra;\n\t"
-      "mov.b64 {%0, %1}, ra; }"
-      : "+f"(a0), "+f"(a1)
-      : "f"(g0), "f"(g1), "f"(f0), "f"(f1));
-}
-
-// red.global.add.v4.f32 (sm_90+): one 16-byte reduction, no return value.
-__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
-// red.global.add.noftz.v4.bf16x2 (sm_90+): eight bf16 lanes in one 16-byte reduction.
-__device__ __forceinline__ void red_add_bf16x8(void* addr, unsigned a, unsigned b, unsigned c, unsigned d) {
-  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
-               : "memory");
-}
+#include "msda_common.cuh"
 
 template <int NT, int LPP, int QPG>
 struct Tile {
@@ -353,6 +209,95 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
         for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
       }
     }
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    uint4* o = reinterpret_cast<uint4*>(p.out) + (((long long)b * p.Q + q) * p.H + h) * LPP + c;
+    *o = Vec16<VT>::pack(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward, HPB heads per block (round 2)
+// ---------------------------------------------------------------------------------------------
+// Measured (profiles/r02_micro2.log): the L1 data array is banked like shared memory, and a warp-wide 128-bit load is
+// served a quarter-warp (8 lanes) at a time. One head's D*sizeof(T) = 64-byte run always lies in the SAME half of its
+// 128-byte line (offset h*64 inside the 512-byte pixel row), so two lane groups of one head always collide: 2
+// wavefronts per quarter-warp, a 64 B/clk/SM ceiling -- msda_fwd_kernel runs at 73 % of exactly that. Here the lane
+// groups of a block alternate between an even and an odd head, so the two 64-byte runs of every quarter-warp fall into
+// different halves and the request is conflict-free (127 B/clk/SM measured). It also makes every fetched 128-byte line
+// fully useful. Virtual query v = ql * HPB + hl  <->  query q0 + ql, head h0 + hl.
+template <typename VT, typename AT, int D, int NT, int QPG, int HPB>
+__global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant__ KParams p) {
+  constexpr int VEC = Vec16<VT>::N;
+  constexpr int LPP = D / VEC;
+  constexpr int NG = NT / LPP, TV = NG * QPG, TQ = TV / HPB, ROW = TV + 1;
+  static_assert(NG % HPB == 0 && TV % HPB == 0, "lane groups must split evenly over the heads");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* sw = reinterpret_cast<float4*>(smem_raw);                                         // [LP][ROW] slot weights * attn
+  int* soff = reinterpret_cast<int*>(smem_raw + (size_t)p.LP * ROW * sizeof(float4));       // [LP][ROW]
+
+  int bid = blockIdx.x;
+  const int hgroups = p.H / HPB;
+  const int h0 = (bid % hgroups) * HPB;
+  bid /= hgroups;
+  const int tile = bid % p.num_tiles;
+  const int b = bid / p.num_tiles;
+  const int q0 = tile * TQ;
+  const int nq = min(TQ, p.Q - q0);
+  const int nv = nq * HPB;
+  const int LP = p.LP;
+
+  // ---- phase 1: descriptors (the LP samples of the HPB heads of one query are adjacent in memory)
+  for (int i = threadIdx.x; i < nv * LP; i += NT) {
+    const int v = i / LP, s = i - v * LP;
+    const int ql = v / HPB, h = h0 + v % HPB;
+    const int l = s / p.P;
+    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+    const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
+    const Level lv = p.lv[l];
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
+    const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
+    const bool ok = ax.ok && ay.ok;
+    const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
+    sw[s * ROW + v] = make_float4(wt * ax.s0, wt * ax.s1, wb * ax.s0, wb * ax.s1);
+    soff[s * ROW + v] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+  }
+  __syncthreads();
+
+  // ---- phase 2: gather
+  const int g = threadIdx.x / LPP, c = threadIdx.x % LPP;
+  const uint4* vb = reinterpret_cast<const uint4*>(p.value) + (long long)b * p.batch_stride16 + c;
+#pragma unroll
+  for (int it = 0; it < QPG; ++it) {
+    const int v = g + it * NG;
+    if (v >= nv) break;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int l = 0; l < p.L; ++l) {
+      const int dx = p.lv[l].dx16, dy = p.lv[l].dy16;
+#pragma unroll 4
+      for (int pt = 0; pt < p.P; ++pt) {
+        const int s = l * p.P + pt;
+        const float4 w = sw[s * ROW + v];
+        const uint4* ptr = vb + soff[s * ROW + v];
+        const uint4 v00 = ldg16(ptr), v01 = ldg16(ptr + dx), v10 = ldg16(ptr + dy), v11 = ldg16(ptr + dy + dx);
+        float f[VEC];
+        Vec16<VT>::unpack(v00, f);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.x, f[j], f[j + 1]);
+        Vec16<VT>::unpack(v01, f);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.y, f[j], f[j + 1]);
+        Vec16<VT>::unpack(v10, f);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.z, f[j], f[j + 1]);
+        Vec16<VT>::unpack(v11, f);
+#pragma unroll
+        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
+      }
+    }
+    const int ql = v / HPB, h = h0 + v % HPB;
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     uint4* o = reinterpret_cast<uint4*>(p.out) + (((long long)b * p.Q + q) * p.H + h) * LPP + c;
     *o = Vec16<VT>::pack(acc);
@@ -605,6 +550,8 @@ int validate(const msda_b200_desc* d) {
   const long long per_batch = (long long)d->S * d->H * d->D * (long long)dtype_size(d->value_dtype) / 16;
   if (per_batch >= (1ll << 31)) return fail(MSDA_B200_ERR_UNSUPPORTED, "S*H*D too large for 32-bit tile offsets");
   if ((long long)d->L * d->P > 64) return fail(MSDA_B200_ERR_UNSUPPORTED, "L*P=%d exceeds 64", d->L * d->P);
+  if (d->tile_start && (d->num_tiles <= 0 || d->max_tile <= 0))
+    return fail(MSDA_B200_ERR_INVALID, "tile schedule with num_tiles=%d, max_tile=%d", d->num_tiles, d->max_tile);
   return MSDA_B200_OK;
 }
 
@@ -655,6 +602,42 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   return check_launch("msda_b200_forward");
 }
 
+// Forward with two heads per block (see msda_fwd_pair_kernel). NT / QPG from the environment for tuning runs only.
+template <typename VT, typename AT, int D, int NT, int QPG>
+int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
+  constexpr int HPB = 2;
+  constexpr int LPP = D / Vec16<VT>::N, NG = NT / LPP, TV = NG * QPG, TQ = TV / HPB, ROW = TV + 1;
+  fill_geometry(d, p, TQ);
+  const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int));
+  auto kern = msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB>;
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
+  const long long blocks = (long long)p.B * p.num_tiles * (p.H / HPB);
+  if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "forward: grid too large");
+  {
+    ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_FWD, st);
+    kern<<<(unsigned)blocks, NT, smem, st>>>(p);
+    ++g_launches;
+  }
+  return check_launch("msda_b200_forward (head pairs)");
+}
+
+int env_cfg(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <typename VT, typename AT, int D>
+int launch_fwd_pair(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
+  const int nt = env_cfg("MSDA_B200_FWD_NT", 128), qpg = env_cfg("MSDA_B200_FWD_QPG", 2);
+  if (nt == 256 && qpg == 2) return launch_fwd_pair_cfg<VT, AT, D, 256, 2>(d, p, st);
+  if (nt == 256 && qpg == 1) return launch_fwd_pair_cfg<VT, AT, D, 256, 1>(d, p, st);
+  if (nt == 128 && qpg == 4) return launch_fwd_pair_cfg<VT, AT, D, 128, 4>(d, p, st);
+  if (nt == 128 && qpg == 1) return launch_fwd_pair_cfg<VT, AT, D, 128, 1>(d, p, st);
+  return launch_fwd_pair_cfg<VT, AT, D, 128, 2>(d, p, st);
+}
+
 template <typename VT, typename AT, int D, int ACC, bool FUSED>
 int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int LPP = D / Vec16<VT>::N;
@@ -680,6 +663,10 @@ int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
 
 template <typename VT, typename AT, bool FUSED>
 int dispatch_fwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
+  if constexpr (!FUSED && std::is_same<VT, __nv_bfloat16>::value) {
+    // 64-byte rows (bf16, D = 32): pair an even with an odd head (bank-conflict-free quarter-warps)
+    if (d->D == 32 && d->H % 2 == 0 && !env_cfg("MSDA_B200_FWD_NO_PAIR", 0)) return launch_fwd_pair<VT, AT, 32>(d, p, st);
+  }
   switch (d->D) {
     case 8: return launch_fwd<VT, AT, 8, FUSED>(d, p, st);
     case 128: return launch_fwd<VT, AT, 128, FUSED>(d, p, st);
@@ -742,6 +729,16 @@ int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
 
 template <bool FUSED>
 int run_forward(const msda_b200_desc* desc, const KParams& p, cudaStream_t st) {
+  if (!FUSED && msda_b200_internal_win_applicable(desc, p.q_order)) {
+    KParams w = p;
+    fill_geometry(desc, w, 1);
+    {
+      ProfScope ps((desc->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_FWD, st);
+      if (int rc = msda_b200_internal_win_forward(desc, &w, st)) return rc;
+      ++g_launches;
+    }
+    return check_launch("msda_b200_forward (window)");
+  }
   const bool vbf = desc->value_dtype == MSDA_B200_BF16, abf = desc->attn_dtype == MSDA_B200_BF16;
   if (!vbf) return dispatch_fwd<float, float, FUSED>(desc, p, st);
   if (abf) return dispatch_fwd<__nv_bfloat16, __nv_bfloat16, FUSED>(desc, p, st);
