@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other location distributions and fp32")
+    ap.add_argument("--no-train", action="store_true", help="skip the `train` block (config 3 DDP fine-tune step)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip timing the reference function on the GPU")
     return ap.parse_args()
 
 
@@ -63,11 +65,27 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def library_source_hash():
+    """sha256 over the CUDA sources the library is built from (what an ncu capture has to be taken on)."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "weed_instance_segmentation_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def recorded_traffic(kernel):
-    """dram bytes per launch from the committed ncu capture, if one has been recorded."""
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json) -- only if that capture was taken
+    on the library built from today's sources (the file carries their hash); a stale capture reads as null."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(kernel)
+            rec = json.load(f)
+        if rec.get("source_hash") != library_source_hash():
+            return None
+        return rec.get(kernel)
     except Exception:
         return None
 
@@ -152,30 +170,30 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    # one image (B=1 of the B=8 batch) with ALL its queries per step: the same per-image work as the b200 arm, fp32
     step, nq = reference_step_fn(1)
+    step()  # cold call (imports, allocator) -- never timed, never used for sizing
     t0 = time.perf_counter()
     step()
     t1 = time.perf_counter() - t0
-    # keep the whole run within a few minutes: shrink the query sample if K steps would not fit
-    budget = 150.0
-    frac = 1.0
-    total = (args.steps + args.warmup) * t1
-    if total > budget:
-        frac = max(1.0 / 16.0, budget / total)
-        step, nq = reference_step_fn(1, frac)
-    for _ in range(args.warmup):
+    warmup, steps = args.warmup, args.steps
+    budget = 170.0  # keep the whole run within a few minutes: fewer steps, never fewer queries
+    if (warmup + steps) * t1 > budget:
+        warmup = min(warmup, 2)
+        steps = max(3, int((budget - warmup * t1) / t1))
+    for _ in range(warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
     S = sum(h * w for h, w in SHAPES_C2)
-    images = nq / S
-    value = images / dt
-    sample = f"1 image (B=1 of the B=8 batch), {nq} of {S} queries per step, fp32, autograd backward"
+    value = 1.0 / dt
+    sample = (f"{steps} steps of 1 image each (B=1 of the B=8 batch, all {nq} of {S} queries), reference HF function "
+              f"M2F:798-837 in fp32 with autograd backward, {dt * 1e3:.0f} ms per image")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config("init", "fp32"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
@@ -326,6 +344,67 @@ def e2e_autograd_steps(torch, wis, prob, steps, warmup, barrier):
     return time_steps(torch, step, steps, warmup, barrier)
 
 
+def gpu_reference_ms(torch, prob, autocast_bf16, iters=3):
+    """The reference's own function (M2F:798-837) + autograd on THIS GPU: ms per fwd+bwd of the whole B=8 batch, run in
+    slices of 2 images to bound its (B*H, D, Q, L*P) temporary (2 GB at B=8, M2F:833). fp32, or under autocast(bf16)."""
+    from oracle.hf_reference import hf_forward_torch
+    dt = torch.bfloat16 if autocast_bf16 else torch.float32
+    v = prob.value.detach().to(dt)
+    lo, a, go = prob.loc.detach(), prob.attn.detach().to(dt), prob.go.detach().to(dt)
+
+    def step():
+        for b0 in range(0, prob.batch, 2):
+            sl = slice(b0, b0 + 2)
+            rv, rl, ra = (t[sl].clone().requires_grad_(True) for t in (v, lo, a))
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast_bf16):
+                out = hf_forward_torch(rv, prob.shapes, rl, ra)
+            out.backward(go[sl].to(out.dtype))
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def copy_ceiling(torch, prob, steps, barrier):
+    """Bare duplex copy of one step's e2e bytes (pinned H2D of the inputs on one stream, D2H of the results on another),
+    every rank at once: the host-side ceiling the pipelined e2e leg can at best reach on this box."""
+    host_in = [t.detach().cpu().pin_memory() for t in (prob.value, prob.loc, prob.attn, prob.go)]
+    dev_out = [prob.out, prob.gv, prob.gl, prob.ga]
+    host_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in dev_out]
+    dev_in = [torch.empty_like(t, device="cuda") for t in host_in]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step():
+        with torch.cuda.stream(s_in):
+            for d, h in zip(dev_in, host_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for h, d in zip(host_out, dev_out):
+                h.copy_(d, non_blocking=True)
+
+    def finish():
+        torch.cuda.current_stream().wait_stream(s_in)
+        torch.cuda.current_stream().wait_stream(s_out)
+
+    def fork():
+        s_in.wait_stream(torch.cuda.current_stream())
+        s_out.wait_stream(torch.cuda.current_stream())
+
+    def stepf():
+        fork()
+        step()
+
+    secs = time_steps(torch, stepf, steps, 2, barrier, finish=finish)
+    nbytes = sum(t.numel() * t.element_size() for t in host_in)
+    return secs / steps, nbytes
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -376,7 +455,7 @@ def run_b200(args, rank, world, local_rank):
     roofline = {
         "bound": "hbm",
         "kernel": ("msda_bwd_sorted_kernel" if (args.dtype == "bf16" and not (prob.flags & _cabi.FLAG_BWD_V1))
-                   else "msda_bwd_kernel") if dominant == "bwd_main" else "msda_fwd_kernel",
+                   else "msda_bwd_kernel") if dominant == "bwd_main" else "msda_fwd_pair_kernel",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms, "traffic": recorded_traffic(dominant),
     }
@@ -398,6 +477,12 @@ def run_b200(args, rank, world, local_rank):
            "d2h_bytes_per_step": d2h, "steps": e2e_k, "ms_per_step": e2e_secs / e2e_k * 1e3,
            "api": "weed_instance_segmentation_b200.HostPipeline.step (msda_b200_host_pipeline_step), pinned host "
                   "buffers, 2 images per chunk, 3 staging slots"}
+    ceil_secs, ceil_bytes = copy_ceiling(torch, prob, e2e_k, barrier)
+    ceil_secs = max_over_ranks(ceil_secs)
+    e2e["copy_ceiling"] = {
+        "what": "bare duplex pinned copy of one step's bytes (H2D inputs + D2H results on two streams), all ranks at once",
+        "ms_per_step": ceil_secs * 1e3, "images_per_s": world * B_PER_GPU / ceil_secs,
+        "gbs_per_direction_per_rank": ceil_bytes / ceil_secs / 1e9, "fraction_reached": ceil_secs / (e2e_secs / e2e_k)}
     ag_secs = max_over_ranks(e2e_autograd_steps(torch, wis, prob, 3, 3, barrier))
     e2e["unpipelined"] = {"value": world * B_PER_GPU * 3 / ag_secs, "ms_per_step": ag_secs / 3 * 1e3,
                           "api": "torch copies + ms_deform_attn + autograd backward on one stream"}
@@ -448,6 +533,26 @@ def run_b200(args, rank, world, local_rank):
                         "sample": f"{n} fwd+bwd steps of 1 image (B=1 of the B=8 batch, all {nq} queries), reference "
                                   f"HF function M2F:798-837 in fp32 with autograd, {dt * 1e3:.0f} ms per image"}
 
+    gpu_reference = None
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        ref32 = gpu_reference_ms(torch, prob, False)
+        ref16 = gpu_reference_ms(torch, prob, True)
+        gpu_reference = {
+            "what": "the reference's function (transformers M2F:798-837) + autograd on the same B200, same B=8 batch in "
+                    "slices of 2 images (bounds its 2 GB temporary), CUDA events",
+            "fp32_ms_per_step": ref32, "autocast_bf16_ms_per_step": ref16,
+            "fp32_images_per_s": B_PER_GPU / ref32 * 1e3, "autocast_bf16_images_per_s": B_PER_GPU / ref16 * 1e3,
+            "speedup_vs_fp32": ref32 / ms_step, "speedup_vs_autocast_bf16": ref16 / ms_step}
+        torch.cuda.empty_cache()
+
+    train_block = None
+    if not args.no_train:
+        # every rank takes part (DDP gradient all-reduce over NCCL); the op buffers are released first
+        del prob
+        torch.cuda.empty_cache()
+        from weed_instance_segmentation_b200 import train as wtrain
+        train_block = wtrain.bench_block(device, world, rank)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -456,7 +561,7 @@ def run_b200(args, rank, world, local_rank):
             "config": workload_config(args.dist, args.dtype),
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
-            "clocks": clocks.summary(), "other_workloads": extras,
+            "clocks": clocks.summary(), "other_workloads": extras, "gpu_reference": gpu_reference, "train": train_block,
         }
         print(json.dumps(line), flush=True)
 

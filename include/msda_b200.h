@@ -67,6 +67,10 @@ extern "C" {
 #define MSDA_B200_FLAG_BWD_V1 4u         /* backward: force the per-corner reduction kernel (v1)  */
                                          /* instead of the pixel-sorted kernel (v2, D=32 & P=4)  */
 #define MSDA_B200_FLAG_NO_WINDOW 8u      /* never use the window-staged (TMA) kernels of msda_win.cu */
+#define MSDA_B200_FLAG_STRICT_PADDING 16u /* forward: skip the FMA of every zero-weight corner, so a non-finite  */
+                                         /* value in a pixel grid_sample's zeros padding never reads (M2F:823)  */
+                                         /* cannot become 0 * Inf = NaN; 25-30 % slower (the backward kernels    */
+                                         /* always treat out-of-level corners as unread)                         */
 
 /* Problem description: plain old data, filled by the caller on the host. */
 typedef struct msda_b200_desc {
@@ -135,13 +139,17 @@ int msda_b200_backward(const msda_b200_desc* desc, const void* value /*dev*/, co
  *   attn_out (optional, float32, (B,Q,H,L,P)): the softmax output, for callers that return it (M2F:983).
  * The backward writes grad_offsets / grad_logits (dtype = attn_dtype); reference points get no gradient
  * (they are constants of the geometry, M2F:1095-1125).
+ * ref_points may be NULL when Q == S and the levels are packed as level_start_index says (the pixel decoder's
+ * self-attention: query i sits on pixel i): the kernels then compute the reference point of a query from its index --
+ * the centre of its own pixel, (x + 0.5) / W_q, (y + 0.5) / H_q, for every level -- which is what
+ * Mask2FormerPixelDecoderEncoderOnly.get_reference_points (M2F:1095-1125) returns for valid_ratios == 1 (no padding).
  */
 int msda_b200_forward_fused(const msda_b200_desc* desc, const void* value /*dev*/, const void* offsets /*dev*/,
-                            const void* logits /*dev*/, const float* ref_points /*dev*/, void* out /*dev*/,
+                            const void* logits /*dev*/, const float* ref_points /*dev|NULL*/, void* out /*dev*/,
                             float* attn_out /*dev|NULL*/, const int32_t* query_order /*dev|NULL*/, void* stream);
 
 int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value /*dev*/, const void* offsets /*dev*/,
-                             const void* logits /*dev*/, const float* ref_points /*dev*/, const void* grad_out /*dev*/,
+                             const void* logits /*dev*/, const float* ref_points /*dev|NULL*/, const void* grad_out /*dev*/,
                              void* grad_value /*dev*/, void* grad_offsets /*dev*/, void* grad_logits /*dev*/,
                              void* workspace /*dev|NULL*/, size_t workspace_bytes,
                              const int32_t* query_order /*dev|NULL*/, void* stream);

@@ -130,6 +130,33 @@ def test_fused_matches_unfused_bitwise_forward(wis):
     assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shapes", [[(8, 8), (16, 16), (32, 32)], [(31, 41), (61, 81), (121, 162)], [(1, 1), (1, 9), (7, 1)]],
+                         ids=["pyramid", "config3", "one_pixel"])
+def test_implicit_reference_points_equal_the_reference_ones_bitwise(wis, shapes, dtype):
+    """reference_points=None (Q == S): the kernels derive each query's reference point from its index. The result
+    must be bit-identical to passing the tensor the reference's own get_reference_points (M2F:1095-1125) builds for
+    un-padded inputs -- forward and all three gradients."""
+    from transformers.models.mask2former.modeling_mask2former import Mask2FormerPixelDecoderEncoderOnly as Enc
+    value, off, logits, _, go = _inputs(2, shapes, 8, 32, 4, None, seed=12)
+    L = len(shapes)
+    ref = Enc.get_reference_points(shapes, torch.ones(2, L, 2, device="cuda"), "cuda")
+    res = []
+    for r in (ref, None):
+        v = value.cuda().to(dtype).requires_grad_(True)
+        o = off.cuda().to(dtype).requires_grad_(True)
+        lg = logits.cuda().to(dtype).requires_grad_(True)
+        out = wis.ms_deform_attn_fused(v, shapes, None, o, lg, r)
+        out.backward(go.cuda().to(dtype))
+        res.append((out.detach(), v.grad, o.grad, lg.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        # gradients: same arithmetic, but the accumulation into grad_value uses atomics (summation order)
+        assert rel_err(b.float().cpu().numpy(), a.float().cpu().numpy()) <= (2e-6 if dtype == torch.float32 else 1e-2)
+    with pytest.raises(ValueError):  # implicit reference points need Q == S
+        wis.ms_deform_attn_fused(value.cuda(), shapes, None, off.cuda()[:, :5], logits.cuda()[:, :5], None)
+
+
 def test_fused_errors(wis):
     v = torch.zeros(1, 16, 8, 32, device="cuda")
     off = torch.zeros(1, 16, 8, 1, 4, 2, device="cuda")

@@ -259,6 +259,79 @@ def test_nan_and_far_locations_are_safe(wis):
     _assert_close(got, want, FP32_BAR, "nan")
 
 
+WINDOW_CASES = [
+    ("c1_pyramid", 2, [(16, 16), (32, 32), (64, 64)]),
+    ("c3_odd", 1, [(31, 41), (61, 81), (121, 162)]),
+    ("two_levels", 2, [(5, 7), (9, 4)]),
+    ("one_pixel_levels", 2, [(1, 1), (1, 9), (7, 1), (4, 4)]),
+]
+
+
+@pytest.mark.parametrize("kernel", ["0", "1"], ids=["cuda_core", "tensor_core"])
+@pytest.mark.parametrize("dist", ["init", "trained", "adversarial"])
+@pytest.mark.parametrize("case", WINDOW_CASES, ids=[c[0] for c in WINDOW_CASES])
+def test_window_staged_forward(wis, case, dist, kernel, monkeypatch):
+    """The opt-in window-staged forward kernels (csrc/msda_win.cu: TMA box loads into shared memory, gather from there,
+    on CUDA cores or through ldmatrix + mma.sync) against the oracle -- including samples that fall outside the
+    staged window (adversarial) and levels smaller than the window."""
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    monkeypatch.setenv("MSDA_B200_WINDOW", "1")
+    monkeypatch.setenv("MSDA_B200_WIN_KERNEL", kernel)
+    tag, B, shapes = case
+    x = msda_inputs(B, shapes, dist=dist, seed=31, value_dtype=torch.bfloat16)
+    out = wis.ms_deform_attn(x["value"].cuda(), shapes, None, x["sampling_locations"].cuda(), x["attention_weights"].cuda())
+    want = oracle.c_forward(x["value"].float().numpy(), shapes, x["sampling_locations"].numpy(),
+                            x["attention_weights"].float().numpy(), dtype=np.float64)
+    assert rel_err(out.float().cpu().numpy(), want) <= BF16_BAR, f"{tag}/{dist}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_non_finite_values_outside_the_footprint_do_not_leak(wis, dtype, monkeypatch):
+    """grid_sample's zeros padding never reads a pixel outside the level, and a sample only reads the (up to four)
+    in-bounds pixels of its own footprint (M2F:823). Every pixel NO sample reads is filled with NaN / Inf here --
+    in particular the clamped neighbours the kernels could load for a border sample -- and the results must still
+    equal the oracle's, finite everywhere except the gradient of the planted pixels (which is exactly zero).
+    Forward: under MSDA_B200_FLAG_STRICT_PADDING (the default forward trades this for speed, see the header);
+    backward: always."""
+    from weed_instance_segmentation_b200 import functional as F
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    monkeypatch.setattr(F, "_STRICT_PADDING", True)
+    shapes = [(8, 9), (10, 6), (1, 12)]
+    H, D, P = 2, 32, 4
+    x = msda_inputs(1, shapes, num_heads=H, head_dim=D, num_points=P, dist="adversarial", seed=11, num_queries=4,
+                    value_dtype=dtype)
+    loc = x["sampling_locations"].clone()
+    loc.view(-1, 2)[::5] = torch.tensor([0.02, 0.97])   # footprints hanging over two borders
+    loc.view(-1, 2)[1::5] = torch.tensor([-0.06, 0.5])  # px in (-1, -0.5): only the right-hand pixels are in bounds
+    value = x["value"].clone()
+    touched = torch.zeros(value.shape[:3], dtype=torch.bool)  # (B, S, H)
+    start = 0
+    for l, (hh, ww) in enumerate(shapes):
+        px = loc[0, :, :, l, :, 0].double() * ww - 0.5  # (Q, H, P)
+        py = loc[0, :, :, l, :, 1].double() * hh - 0.5
+        x0, y0 = torch.floor(px).long(), torch.floor(py).long()
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xx, yy = x0 + dx, y0 + dy
+                ok = (xx >= 0) & (xx < ww) & (yy >= 0) & (yy < hh)
+                for h in range(H):
+                    idx = (start + yy[:, h] * ww + xx[:, h])[ok[:, h]]
+                    touched[0, idx, h] = True
+        start += hh * ww
+    assert (~touched).sum() > 10
+    bad = torch.tensor([float("nan"), float("inf"), float("-inf")]).to(dtype)
+    planted = value.clone()
+    planted[~touched] = bad[torch.arange((~touched).sum()) % 3][:, None].expand(-1, D)
+    args = (planted, shapes, loc, x["attention_weights"], x["grad_out"])
+    got = _run(wis, *args)
+    want = _oracle(value, shapes, loc, x["attention_weights"], x["grad_out"],
+                   dtype=np.float32 if dtype == torch.float32 else np.float64)  # the oracle on the clean values
+    assert all(np.isfinite(g).all() for g in got), "a non-finite value leaked out of a pixel the reference never reads"
+    bar = FP32_BAR if dtype == torch.float32 else BF16_BAR
+    _assert_close(got, want, bar, "planted", safe=_kink_safe(loc.numpy(), shapes), min_safe=0.5)
+    assert not got[1][~touched.numpy()].any()  # no gradient reaches a pixel nobody reads
+
+
 # ---------------------------------------------------------------------------- full-size properties
 def _c2_inputs(dist, dtype):
     from weed_instance_segmentation_b200.synth import msda_inputs

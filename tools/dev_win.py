@@ -69,6 +69,16 @@ def main():
         def f_new():
             _cabi.check(lib.msda_b200_forward(d_new, ptr(value), ptr(loc), ptr(attn), ptr(out_new), ptr(sched.order), stream))
 
+        if what == "bwd":  # backward timing through the C ABI
+            gv, gl, ga = torch.empty_like(value), torch.empty_like(loc), torch.empty_like(attn)
+            nws = int(lib.msda_b200_backward_workspace_bytes(d_old))
+            ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+
+            def f_bwd():
+                _cabi.check(lib.msda_b200_backward(d_old, ptr(value), ptr(loc), ptr(attn), ptr(go), ptr(gv), ptr(gl), ptr(ga),
+                                                   ptr(ws), nws, ptr(order), stream))
+            print(f"{tag:18s} backward {timed(f_bwd):.3f} ms   forward {timed(f_old):.3f} ms", flush=True)
+            continue
         if what == "onebwd":  # a few launches of the backward on config 2 / init, for an ncu capture
             gv, gl, ga = torch.empty_like(value), torch.empty_like(loc), torch.empty_like(attn)
             nws = int(lib.msda_b200_backward_workspace_bytes(d_old))

@@ -77,11 +77,24 @@ __device__ __forceinline__ void store_pair<__nv_bfloat16>(void* base, long long 
   reinterpret_cast<__nv_bfloat162*>(base)[idx] = __floats2bfloat162_rn(x, y);
 }
 
+// Reference point of query q when the caller passes none (ref == NULL; requires Q == S): the query IS pixel q of its
+// level and its reference point is the centre of that pixel, the same for every level -- what
+// Mask2FormerPixelDecoderEncoderOnly.get_reference_points (M2F:1095-1125) computes with valid_ratios == 1:
+// linspace(0.5, n - 0.5, n)[i] / n = (i + 0.5) / n in fp32, bit for bit.
+__device__ __forceinline__ float2 implicit_reference_point(const KParams& p, int q) {
+  int lq = 0;
+  for (int l = 1; l < p.L; ++l)
+    if (q >= p.lv[l].start) lq = l;  // levels are stored in increasing row order
+  const int r = q - p.lv[lq].start, W = p.lv[lq].W, H = p.lv[lq].H;
+  const int y = r / W, x = r - y * W;
+  return make_float2(__fdiv_rn((float)x + 0.5f, (float)W), __fdiv_rn((float)y + 0.5f, (float)H));
+}
+
 // si: global sample index ((b*Q+q)*H+h)*LP + s; ri: reference-point index (b*Q+q)*L + l
 template <typename AT>
-__device__ __forceinline__ float2 fused_loc(const KParams& p, long long si, long long ri, const Level& lv) {
+__device__ __forceinline__ float2 fused_loc(const KParams& p, long long si, long long ri, int q, const Level& lv) {
   const float2 off = load_pair<AT>(p.offsets, si);
-  const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref) + ri);
+  const float2 r = p.ref ? __ldg(reinterpret_cast<const float2*>(p.ref) + ri) : implicit_reference_point(p, q);
   return make_float2(__fadd_rn(r.x, __fdiv_rn(off.x, (float)lv.W)), __fadd_rn(r.y, __fdiv_rn(off.y, (float)lv.H)));
 }
 
@@ -112,32 +125,102 @@ __device__ __forceinline__ void softmax_stats_x4(const AT* lg, int LP, int sub, 
   inv = valid ? 1.f / sum : 0.f;
 }
 
-// softmax of the tile's (query, head) rows into shared memory, four lanes per query
-template <typename AT, int NT>
-__device__ __forceinline__ void tile_softmax(const KParams& p, int b, int h, int q0, int nq, float* s_att, bool write_out) {
+// softmax of the tile's (query, head) rows into shared memory, four lanes per row; row v = ql * HPB + hl is query
+// q0 + ql, head h0 + hl. Each lane keeps its (up to four) logits in registers: ONE expf per logit (rows longer than
+// 16 logits take the three-pass form).
+template <typename AT, int NT, int HPB>
+__device__ __forceinline__ void tile_softmax(const KParams& p, int b, int h0, int q0, int nq, float* s_att, bool write_out) {
   const int LP = p.LP;
   const int sub = threadIdx.x & 3;
-  for (int qb = 0; qb < nq; qb += NT / 4) {
-    const int ql = qb + (threadIdx.x >> 2);
-    const bool valid = ql < nq;
+  const int nv = nq * HPB;
+  for (int vb0 = 0; vb0 < nv; vb0 += NT / 4) {
+    const int v = vb0 + (threadIdx.x >> 2);
+    const bool valid = v < nv;
+    const int ql = v / HPB, h = h0 + v % HPB;
     const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
     const long long row = (((long long)b * p.Q + q) * p.H + h) * LP;
     const AT* lg = reinterpret_cast<const AT*>(p.logits) + row;
-    float mx, inv;
-    softmax_stats_x4<AT>(lg, LP, sub, valid, mx, inv);
-    if (valid)
-      for (int s = sub; s < LP; s += 4) {
-        const float a = expf(to_float<AT>(lg[s]) - mx) * inv;
-        s_att[ql * LP + s] = a;
-        if (write_out && p.attn_out) p.attn_out[row + s] = a;
+    if (LP <= 16) {
+      float e[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int s = sub + 4 * r;
+        e[r] = (valid && s < LP) ? to_float<AT>(lg[s]) : -INFINITY;
+        mx = fmaxf(mx, e[r]);
       }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        e[r] = (valid && sub + 4 * r < LP) ? expf(e[r] - mx) : 0.f;
+        sum += e[r];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int s = sub + 4 * r;
+        if (valid && s < LP) {
+          const float a = e[r] * inv;
+          s_att[v * LP + s] = a;
+          if (write_out && p.attn_out) p.attn_out[row + s] = a;
+        }
+      }
+    } else {
+      float mx, inv;
+      softmax_stats_x4<AT>(lg, LP, sub, valid, mx, inv);
+      if (valid)
+        for (int s = sub; s < LP; s += 4) {
+          const float a = expf(to_float<AT>(lg[s]) - mx) * inv;
+          s_att[v * LP + s] = a;
+          if (write_out && p.attn_out) p.attn_out[row + s] = a;
+        }
+    }
+  }
+}
+
+// One sample for one lane: four 16-byte corner loads and the weighted accumulation.
+// STRICT = false (default): a slot outside the level has weight exactly 0 but is still loaded from the clamped pixel
+//   next to it and multiplied. With finite activations that is grid_sample's zeros padding (M2F:823) exactly.
+// STRICT = true (MSDA_B200_FLAG_STRICT_PADDING): the FMA of a zero-weight corner is skipped, so a non-finite value in
+//   a pixel the reference never reads cannot turn into 0 * Inf = NaN. Measured on B200 (profiles/r02_notes.md): every
+//   way of guarding the corner costs 25-30 % of the forward (0.29 -> 0.38 ms): a branch per corner stops the compiler
+//   from overlapping the loads of neighbouring samples, and ptxas lowers a predicated FFMA2 to FFMA2 + two SELs.
+//   Hence a flag, not the default. (An in-bounds corner whose weight is exactly 0 is skipped too; the reference
+//   multiplies it, which differs only if that pixel is itself non-finite.)
+template <typename VT, int VEC, bool STRICT>
+__device__ __forceinline__ void gather_sample(const uint4* ptr, int dx, int dy, const float4& w, float (&acc)[VEC]) {
+  const uint4 v00 = ldg16(ptr), v01 = ldg16(ptr + dx), v10 = ldg16(ptr + dy), v11 = ldg16(ptr + dy + dx);
+  float f[VEC];
+  Vec16<VT>::unpack(v00, f);
+  if (!STRICT || w.x != 0.f) {
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.x, f[j], f[j + 1]);
+  }
+  Vec16<VT>::unpack(v01, f);
+  if (!STRICT || w.y != 0.f) {
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.y, f[j], f[j + 1]);
+  }
+  Vec16<VT>::unpack(v10, f);
+  if (!STRICT || w.z != 0.f) {
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.z, f[j], f[j + 1]);
+  }
+  Vec16<VT>::unpack(v11, f);
+  if (!STRICT || w.w != 0.f) {
+#pragma unroll
+    for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Forward
 // ---------------------------------------------------------------------------------------------
-template <typename VT, typename AT, int D, int NT, int QPG, bool FUSED>
+template <typename VT, typename AT, int D, int NT, int QPG, bool FUSED, bool STRICT>
 __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -154,7 +237,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
   const int LP = p.LP;
 
   if (FUSED) {
-    tile_softmax<AT, NT>(p, b, h, q0, nq, s_att, true);
+    tile_softmax<AT, NT, 1>(p, b, h, q0, nq, s_att, true);
     __syncthreads();
   }
 
@@ -165,7 +248,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
     const Level lv = p.lv[l];
-    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, lv)
+    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, q, lv)
                             : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
     const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
@@ -191,22 +274,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
 #pragma unroll 4
       for (int pt = 0; pt < p.P; ++pt) {
         const int s = l * p.P + pt;
-        const float4 w = sw[s * T::ROW + ql];
-        const uint4* ptr = vb + soff[s * T::ROW + ql];
-        const uint4 v00 = ldg16(ptr), v01 = ldg16(ptr + dx), v10 = ldg16(ptr + dy), v11 = ldg16(ptr + dy + dx);
-        float f[VEC];
-        Vec16<VT>::unpack(v00, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.x, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v01, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.y, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v10, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.z, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v11, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
+        gather_sample<VT, VEC, STRICT>(vb + soff[s * T::ROW + ql], dx, dy, sw[s * T::ROW + ql], acc);
       }
     }
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
@@ -225,7 +293,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
 // groups of a block alternate between an even and an odd head, so the two 64-byte runs of every quarter-warp fall into
 // different halves and the request is conflict-free (127 B/clk/SM measured). It also makes every fetched 128-byte line
 // fully useful. Virtual query v = ql * HPB + hl  <->  query q0 + ql, head h0 + hl.
-template <typename VT, typename AT, int D, int NT, int QPG, int HPB>
+template <typename VT, typename AT, int D, int NT, int QPG, int HPB, bool FUSED>
 __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -234,6 +302,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* sw = reinterpret_cast<float4*>(smem_raw);                                         // [LP][ROW] slot weights * attn
   int* soff = reinterpret_cast<int*>(smem_raw + (size_t)p.LP * ROW * sizeof(float4));       // [LP][ROW]
+  float* s_att = reinterpret_cast<float*>(soff + (size_t)p.LP * ROW);                       // FUSED: [TV][LP] softmax
 
   int bid = blockIdx.x;
   const int hgroups = p.H / HPB;
@@ -246,6 +315,11 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   const int nv = nq * HPB;
   const int LP = p.LP;
 
+  if (FUSED) {
+    tile_softmax<AT, NT, HPB>(p, b, h0, q0, nq, s_att, true);
+    __syncthreads();
+  }
+
   // ---- phase 1: descriptors (the LP samples of the HPB heads of one query are adjacent in memory)
   for (int i = threadIdx.x; i < nv * LP; i += NT) {
     const int v = i / LP, s = i - v * LP;
@@ -254,8 +328,9 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
     const Level lv = p.lv[l];
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.loc) + si);
-    const float a = to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
+    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, q, lv)
+                            : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+    const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
     const bool ok = ax.ok && ay.ok;
     const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
@@ -279,22 +354,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
 #pragma unroll 4
       for (int pt = 0; pt < p.P; ++pt) {
         const int s = l * p.P + pt;
-        const float4 w = sw[s * ROW + v];
-        const uint4* ptr = vb + soff[s * ROW + v];
-        const uint4 v00 = ldg16(ptr), v01 = ldg16(ptr + dx), v10 = ldg16(ptr + dy), v11 = ldg16(ptr + dy + dx);
-        float f[VEC];
-        Vec16<VT>::unpack(v00, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.x, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v01, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.y, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v10, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.z, f[j], f[j + 1]);
-        Vec16<VT>::unpack(v11, f);
-#pragma unroll
-        for (int j = 0; j < VEC; j += 2) fma2_scalar(acc[j], acc[j + 1], w.w, f[j], f[j + 1]);
+        gather_sample<VT, VEC, false>(vb + soff[s * ROW + v], dx, dy, sw[s * ROW + v], acc);
       }
     }
     const int ql = v / HPB, h = h0 + v % HPB;
@@ -331,7 +391,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
   const int nq = min(T::TQ, p.Q - q0);
 
   if (FUSED) {
-    tile_softmax<AT, NT>(p, b, h, q0, nq, s_att, false);
+    tile_softmax<AT, NT, 1>(p, b, h, q0, nq, s_att, false);
     __syncthreads();
   }
 
@@ -342,7 +402,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
     const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
     const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
     const Level lv = p.lv[l];
-    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, lv)
+    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, q, lv)
                             : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
     const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
     const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
@@ -351,7 +411,10 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
     ss[k] = ok ? make_float4(ax.s0, ax.s1, ay.s0, ay.s1) : make_float4(0.f, 0.f, 0.f, 0.f);
     sg[k] = ok ? make_float4(ax.g0, ax.g1, ay.g0, ay.g1) : make_float4(0.f, 0.f, 0.f, 0.f);
     sa[k] = a;
-    soff[k] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+    // a slot outside the level ("dead": derivative code 0) must not be read at all (zeros padding, M2F:823): samples
+    // that have one are flagged in the sign bit and take predicated loads in phase 2
+    const bool all_alive = ok && ax.g0 != 0.f && ax.g1 != 0.f && ay.g0 != 0.f && ay.g1 != 0.f;
+    soff[k] = (((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP) | (all_alive ? 0 : (int)0x80000000);
   }
   __syncthreads();
 
@@ -376,11 +439,20 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
         const int k = s * T::ROW + ql;
         const float4 w = ss[k];
         const float a = sa[k];
-        const int off = soff[k];
+        const int off_flag = soff[k];
+        const int off = off_flag & 0x7fffffff;
         const uint4* ptr = vb + off;
-        const uint4 v[4] = {ldg16(ptr), ldg16(ptr + dx), ldg16(ptr + dy), ldg16(ptr + dy + dx)};
-        const float wc[4] = {a * w.z * w.x, a * w.z * w.y, a * w.w * w.x, a * w.w * w.y};
         const int coff[4] = {0, dx, dy, dy + dx};
+        bool alive[4] = {true, true, true, true};
+        if (off_flag < 0) {
+          const float4 gw = sg[k];
+          alive[0] = gw.x != 0.f && gw.z != 0.f; alive[1] = gw.y != 0.f && gw.z != 0.f;
+          alive[2] = gw.x != 0.f && gw.w != 0.f; alive[3] = gw.y != 0.f && gw.w != 0.f;
+        }
+        uint4 v[4];
+#pragma unroll
+        for (int cn = 0; cn < 4; ++cn) v[cn] = alive[cn] ? ldg16(ptr + coff[cn]) : make_uint4(0u, 0u, 0u, 0u);
+        const float wc[4] = {a * w.z * w.x, a * w.z * w.y, a * w.w * w.x, a * w.w * w.y};
         float dot[4];
 #pragma unroll
         for (int cn = 0; cn < 4; ++cn) {
@@ -390,7 +462,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
 #pragma unroll
           for (int j = 0; j < VEC; ++j) d = fmaf(go[j], f[j], d);
           dot[cn] = d;
-          if (wc[cn] != 0.f) {
+          if (alive[cn] && wc[cn] != 0.f) {
             // element offset of this lane's 16 bytes inside grad_value
             const long long e = ((long long)b * p.batch_stride16 + off + coff[cn] + c) * VEC;
             if (ACC == 0) {
@@ -588,7 +660,9 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   fill_geometry(d, p, T::TQ);
   const size_t smem = (size_t)p.LP * T::ROW * (sizeof(float4) + sizeof(int)) +
                       (FUSED ? (size_t)T::TQ * p.LP * sizeof(float) : 0);
-  auto kern = msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG, FUSED>;
+  const bool strict = (d->flags & MSDA_B200_FLAG_STRICT_PADDING) != 0;
+  auto kern = strict ? msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG, FUSED, true>
+                     : msda_fwd_kernel<VT, AT, D, kFwdNT, kFwdQPG, FUSED, false>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
@@ -603,13 +677,13 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
 }
 
 // Forward with two heads per block (see msda_fwd_pair_kernel). NT / QPG from the environment for tuning runs only.
-template <typename VT, typename AT, int D, int NT, int QPG>
+template <typename VT, typename AT, int D, int NT, int QPG, bool FUSED>
 int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int HPB = 2;
   constexpr int LPP = D / Vec16<VT>::N, NG = NT / LPP, TV = NG * QPG, TQ = TV / HPB, ROW = TV + 1;
   fill_geometry(d, p, TQ);
-  const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int));
-  auto kern = msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB>;
+  const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int)) + (FUSED ? (size_t)TV * p.LP * sizeof(float) : 0);
+  auto kern = msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
@@ -628,14 +702,11 @@ int env_cfg(const char* name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 
-template <typename VT, typename AT, int D>
+template <typename VT, typename AT, int D, bool FUSED>
 int launch_fwd_pair(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
-  const int nt = env_cfg("MSDA_B200_FWD_NT", 128), qpg = env_cfg("MSDA_B200_FWD_QPG", 2);
-  if (nt == 256 && qpg == 2) return launch_fwd_pair_cfg<VT, AT, D, 256, 2>(d, p, st);
-  if (nt == 256 && qpg == 1) return launch_fwd_pair_cfg<VT, AT, D, 256, 1>(d, p, st);
-  if (nt == 128 && qpg == 4) return launch_fwd_pair_cfg<VT, AT, D, 128, 4>(d, p, st);
-  if (nt == 128 && qpg == 1) return launch_fwd_pair_cfg<VT, AT, D, 128, 1>(d, p, st);
-  return launch_fwd_pair_cfg<VT, AT, D, 128, 2>(d, p, st);
+  // 128 threads, 2 (query, head) pairs per lane group measured best on config 2 (ms): 128/2 0.294, 128/1 0.302,
+  // 256/2 0.297, 256/1 0.307, 128/4 0.407; one head per block (msda_fwd_kernel) 0.313
+  return launch_fwd_pair_cfg<VT, AT, D, 128, 2, FUSED>(d, p, st);
 }
 
 template <typename VT, typename AT, int D, int ACC, bool FUSED>
@@ -663,9 +734,10 @@ int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
 
 template <typename VT, typename AT, bool FUSED>
 int dispatch_fwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
-  if constexpr (!FUSED && std::is_same<VT, __nv_bfloat16>::value) {
+  if constexpr (std::is_same<VT, __nv_bfloat16>::value) {
     // 64-byte rows (bf16, D = 32): pair an even with an odd head (bank-conflict-free quarter-warps)
-    if (d->D == 32 && d->H % 2 == 0 && !env_cfg("MSDA_B200_FWD_NO_PAIR", 0)) return launch_fwd_pair<VT, AT, 32>(d, p, st);
+    if (d->D == 32 && d->H % 2 == 0 && !(d->flags & MSDA_B200_FLAG_STRICT_PADDING) && !env_cfg("MSDA_B200_FWD_NO_PAIR", 0))
+      return launch_fwd_pair<VT, AT, 32, FUSED>(d, p, st);
   }
   switch (d->D) {
     case 8: return launch_fwd<VT, AT, 8, FUSED>(d, p, st);
@@ -823,8 +895,9 @@ int msda_b200_forward_fused(const msda_b200_desc* desc, const void* value, const
   g_err[0] = 0;
   if (int rc = validate(desc)) return rc;
   if ((long long)desc->B * desc->Q == 0) return MSDA_B200_OK;
-  if (!value || !offsets || !logits || !ref_points || !out)
-    return fail(MSDA_B200_ERR_INVALID, "forward_fused: NULL tensor pointer");
+  if (!value || !offsets || !logits || !out) return fail(MSDA_B200_ERR_INVALID, "forward_fused: NULL tensor pointer");
+  if (!ref_points && desc->Q != desc->S)
+    return fail(MSDA_B200_ERR_INVALID, "forward_fused: implicit reference points (ref_points = NULL) need Q == S");
   KParams p;
   memset(&p, 0, sizeof(p));
   p.value = value; p.offsets = offsets; p.logits = logits; p.ref = ref_points; p.out = out; p.attn_out = attn_out;
@@ -862,7 +935,9 @@ int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value, cons
   memset(&p, 0, sizeof(p));
   p.value = value; p.offsets = offsets; p.logits = logits; p.ref = ref_points; p.grad_out = grad_out;
   p.grad_offsets = grad_offsets; p.grad_logits = grad_logits; p.q_order = query_order;
-  const bool have = value && offsets && logits && ref_points && grad_out && grad_offsets && grad_logits;
+  if (!ref_points && desc->Q != desc->S)
+    return fail(MSDA_B200_ERR_INVALID, "backward_fused: implicit reference points (ref_points = NULL) need Q == S");
+  const bool have = value && offsets && logits && grad_out && grad_offsets && grad_logits;
   return run_backward<true>(desc, p, grad_value, workspace, workspace_bytes, have, reinterpret_cast<cudaStream_t>(stream));
 }
 

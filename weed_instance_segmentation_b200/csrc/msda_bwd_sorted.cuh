@@ -39,7 +39,7 @@ __host__ __device__ inline SortedSmem sorted_smem_layout() {
   SortedSmem s;
   size_t o = 0;
   s.w = o;    o += sizeof(float4) * NS;
-  s.go = o;   o += sizeof(uint4) * TQ * LPP;
+  s.go = o;   o += sizeof(uint4) * (TQ + 1) * LPP;  // + one all-zero row, read by the padding entries of the pull
   s.ent = o;  o += sizeof(int2) * NC;
   s.dot = o;  o += sizeof(float) * NC;
   s.a = o;    o += sizeof(float) * NS;
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
     }
     s_go[i] = v;
   }
+  if (tid < LPP) s_go[TQ * LPP + tid] = make_uint4(0u, 0u, 0u, 0u);
 
   // per-thread samples: si = r*NT + tid; their loc / attn are prefetched one level ahead
   constexpr int SPT = (NS + NT - 1) / NT;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
         const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
         const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
         if (FUSED) {
-          pre_loc[r] = fused_loc<AT>(p, gi, ((long long)b * p.Q + q) * p.L + l, p.lv[l]);
+          pre_loc[r] = fused_loc<AT>(p, gi, ((long long)b * p.Q + q) * p.L + l, q, p.lv[l]);
           pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]);  // raw logit; softmax applied at use
         } else {
           pre_loc[r] = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) msda_bwd_sorted_kernel(const __
       for (int k = 0; k < per; ++k) {
         const int e = e0 + k;
         const bool valid = e < e_end;
-        int2 en = make_int2(cur << 16, 0);  // padding: same pixel, weight 0, dot discarded
+        // padding: same pixel, weight 0, the all-zero grad_out row (0 * a non-finite grad_out would poison the run), dot discarded
+        int2 en = make_int2((cur << 16) | (TQ << (2 + LP2)), 0);
         if (valid) en = s_ent[e];
         const int pix = (int)((unsigned)en.x >> 16);
         const int id = en.x & 0xffff;

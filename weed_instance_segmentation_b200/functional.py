@@ -40,6 +40,9 @@ _TILE = _parse_tile(os.environ.get("MSDA_B200_TILE", "8x16"))
 _USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "1") != "0"
 _BF16_ATOMICS = os.environ.get("MSDA_B200_BF16_ATOMICS", "0") == "1"
 _BWD_V1 = os.environ.get("MSDA_B200_BWD_V1", "0") == "1"
+# Forward: never multiply a zero-weight corner (exact zeros padding even when `value` holds NaN / Inf in pixels no
+# sample reads; 25-30 % slower, see include/msda_b200.h MSDA_B200_FLAG_STRICT_PADDING).
+_STRICT_PADDING = os.environ.get("MSDA_B200_STRICT_PADDING", "0") == "1"
 
 _order_cache: dict = {}
 _lsi_checked: set = set()
@@ -291,6 +294,8 @@ def ms_deform_attn(
         if _window_eligible(value, sampling_locations):
             sched = pyramid_schedule(shapes, device=value.device)
     flags = _cabi.FLAG_PROFILE if profile else 0
+    if _STRICT_PADDING:
+        flags |= _cabi.FLAG_STRICT_PADDING
     return MSDeformAttnFunction.apply(value, shapes, level_start, sampling_locations, attention_weights, order, flags,
                                       sched)
 

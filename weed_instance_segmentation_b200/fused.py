@@ -44,7 +44,7 @@ class MSDeformAttnFusedFunction(torch.autograd.Function):
         value_c = value.contiguous()
         offsets_c = offsets.to(aux).contiguous()
         logits_c = logits.to(aux).contiguous()
-        ref_c = ref_points.float().contiguous()
+        ref_c = ref_points.float().contiguous() if ref_points is not None else None  # None: computed in the kernels
         B, S, H, D = value_c.shape
         _, Q, _, L, P, _ = offsets_c.shape
         out = torch.empty((B, Q, H * D), dtype=value_c.dtype, device=value_c.device)
@@ -106,12 +106,16 @@ def ms_deform_attn_fused(value, value_spatial_shapes, level_start_index, samplin
         level_start_index: ``(L,)`` or ``None`` (prefix sum of the shapes).
         sampling_offsets: ``(B, Q, H, L, P, 2)`` raw output of the ``sampling_offsets`` projection, in pixels.
         attention_logits: ``(B, Q, H, L*P)`` (or ``(B, Q, H, L, P)``) raw output of the ``attention_weights`` projection.
-        reference_points: ``(B, Q, L, 2)`` normalised ``(x, y)`` (M2F:1095-1125).
+        reference_points: ``(B, Q, L, 2)`` normalised ``(x, y)`` (M2F:1095-1125), or ``None`` when ``Q == S`` (the pixel
+            decoder's self-attention, query i = pixel i): the kernels then derive each query's reference point -- the
+            centre of its own pixel, for every level -- from its index, exactly as ``get_reference_points`` does for
+            un-padded inputs (``valid_ratios == 1``); no reference-point tensor is built or read.
     Returns:
         ``output (B, Q, H*D)`` and, if requested, ``attention_weights (B, Q, H, L, P)`` float32 (no gradient).
     """
     shapes = F._shapes_list(value_spatial_shapes)
-    if not (value.is_cuda and sampling_offsets.is_cuda and attention_logits.is_cuda and reference_points.is_cuda):
+    if not (value.is_cuda and sampling_offsets.is_cuda and attention_logits.is_cuda
+            and (reference_points is None or reference_points.is_cuda)):
         raise RuntimeError("ms_deform_attn_fused: tensors must live on a CUDA device (this package has no CPU fallback)")
     if value.dim() != 4:
         raise ValueError(f"value must be (B, S, H, D), got {tuple(value.shape)}")
@@ -123,12 +127,16 @@ def ms_deform_attn_fused(value, value_spatial_shapes, level_start_index, samplin
         raise ValueError("sampling_offsets / spatial shapes do not match value")
     if attention_logits.numel() != B * Q * H * L * P or attention_logits.shape[:3] != (B, Q, H):
         raise ValueError(f"attention_logits must be {(B, Q, H, L * P)}, got {tuple(attention_logits.shape)}")
-    if reference_points.shape[-1] != 2:
-        raise ValueError(f"Last dim of reference_points must be 2 for the fused op, got {reference_points.shape[-1]}")
-    if tuple(reference_points.shape) != (B, Q, L, 2):
-        reference_points = reference_points.expand(B, Q, L, 2)
-    if reference_points.requires_grad:
-        raise ValueError("ms_deform_attn_fused does not differentiate with respect to reference_points")
+    if reference_points is None:
+        if Q != S or Q != sum(h * w for h, w in shapes):
+            raise ValueError("implicit reference points (reference_points=None) need Q == S == sum of the level sizes")
+    else:
+        if reference_points.shape[-1] != 2:
+            raise ValueError(f"Last dim of reference_points must be 2 for the fused op, got {reference_points.shape[-1]}")
+        if tuple(reference_points.shape) != (B, Q, L, 2):
+            reference_points = reference_points.expand(B, Q, L, 2)
+        if reference_points.requires_grad:
+            raise ValueError("ms_deform_attn_fused does not differentiate with respect to reference_points")
     if sum(h * w for h, w in shapes) > S:
         raise ValueError(f"spatial shapes cover more rows than value has (S={S})")
     if value.dtype not in _DTYPE_CODE:

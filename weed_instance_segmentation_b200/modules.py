@@ -65,6 +65,7 @@ class MSDeformAttn(nn.Module):
         new.assume_no_padding = False
         new.fused_prologue = False
         new.fused_linear = False
+        new.implicit_reference_points = False
         new.train(mod.training)
         return new
 
@@ -106,9 +107,11 @@ class MSDeformAttn(nn.Module):
         sampling_offsets = self._proj(self.sampling_offsets, hidden_states).view(batch_size, num_queries, H, L, P, 2)
         attention_weights = self._proj(self.attention_weights, hidden_states).view(batch_size, num_queries, H, L * P)
         if self.fused_prologue and reference_points.shape[-1] == 2 and not reference_points.requires_grad:
-            # softmax (M2F:955-960) and ref + off / (W, H) (M2F:962-971) happen inside the kernels
+            # softmax (M2F:955-960) and ref + off / (W, H) (M2F:962-971) happen inside the kernels; in the pixel
+            # decoder's self-attention (query i = pixel i, no padding) the reference points (M2F:1095-1125) do too
+            implicit = self.implicit_reference_points and num_queries == sequence_length
             res = ms_deform_attn_fused(value, spatial_shapes_list, level_start_index, sampling_offsets,
-                                       attention_weights, reference_points,
+                                       attention_weights, None if implicit else reference_points,
                                        return_attention_weights=output_attentions)
             output, attention_weights = res if output_attentions else (res, None)
             return self._proj(self.output_proj, output), attention_weights
@@ -229,6 +232,27 @@ class EncoderLayer(nn.Module):
         return outputs
 
 
+def _cached_reference_points(original):
+    """``get_reference_points`` (M2F:1095-1125) for un-padded inputs: ``valid_ratios`` is all ones, so the result is a
+    constant of (shapes, batch, device, dtype) -- computed once with the reference's own code, then reused (the
+    reference rebuilds it, ~20 small kernels, in every forward). The fused kernels do not even read it
+    (``implicit_reference_points``); HF's encoder loop still passes it along."""
+    cache: dict = {}
+
+    def get_reference_points(spatial_shapes_list, valid_ratios, device):
+        key = (tuple(tuple(s) for s in spatial_shapes_list), tuple(valid_ratios.shape), str(device), valid_ratios.dtype)
+        hit = cache.get(key)
+        if hit is None:
+            hit = original(spatial_shapes_list, torch.ones_like(valid_ratios), device).detach()
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = hit
+        return hit
+
+    get_reference_points._b200_cache = cache
+    return get_reference_points
+
+
 def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fused_prologue: bool = True,
                           fused_norm: bool = True, fused_linear: bool = True) -> int:
     """Replace every HF pixel-decoder encoder layer (and its MSDeformAttn) inside ``model`` by the
@@ -242,11 +266,14 @@ def convert_pixel_decoder(model: nn.Module, assume_no_padding: bool = True, fuse
     converted = 0
     for module in model.modules():
         if isinstance(module, m2f.Mask2FormerPixelDecoderEncoderOnly):
+            if assume_no_padding and not hasattr(module.get_reference_points, "_b200_cache"):
+                module.get_reference_points = _cached_reference_points(module.get_reference_points)
             for i, layer in enumerate(module.layers):
                 if isinstance(layer, EncoderLayer):
                     continue
                 new = EncoderLayer.from_hf(layer)
                 new.self_attn.assume_no_padding = assume_no_padding
+                new.self_attn.implicit_reference_points = assume_no_padding and fused_prologue
                 new.self_attn.fused_prologue = fused_prologue
                 new.fused_norm = fused_norm
                 new.fused_linear = new.self_attn.fused_linear = fused_linear

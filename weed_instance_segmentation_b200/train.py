@@ -207,6 +207,56 @@ def throughput(trainer: Trainer, batches: list, steps: int, warmup: int, prefetc
     return secs
 
 
+def bench_block(device, world: int, rank: int, batch: int = 16, height: int = 966, width: int = 1296, classes: int = 3,
+                steps: int = 4, warmup: int = 6, with_stock: bool = True) -> dict:
+    """The ``train`` block of ``bench.py``'s JSON line: BASELINE config 3 (Swin-T fine-tune on 966x1296 synthetic
+    crop_weed-shaped images, ``batch`` per GPU, fp32, AdamW, gradient accumulation 2 with ``no_sync`` on the first
+    micro-batch) through :class:`Trainer` under the caller's process group -- the step of
+    ``/root/reference/models/mask2former/train.py:191-205`` with the DDP gradient all-reduce over NCCL.
+
+    Every rank calls this (DDP is collective). At ``world == 1`` the stock HF model is timed as well.
+    Returns images/s over all ranks (max-over-ranks device time), ms per micro-batch and the all-reduce payload.
+    """
+
+    def run(impl: str, n_steps: int, n_warm: int) -> tuple[float, float, int]:
+        torch.manual_seed(0)
+        model = build_model("swin_t", classes)
+        pinned = impl == "b200"
+        if impl == "b200":
+            use_b200_path(model, "modules", criterion=True)
+        else:
+            hf_patch.uninstall()  # the stock arm must run the reference's own function (M2F:798-837)
+        model.to(device)
+        if world > 1:
+            install_distributed_num_masks()
+        nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        trainer = Trainer(model, device, ddp=world > 1)
+        kw = dict(mask_dtype=torch.uint8, pin_memory=True) if pinned else {}
+        batches = [synth.collate_batch(batch, height, width, classes, seed=rank * 1000 + i, **kw) for i in range(2)]
+        secs = throughput(trainer, batches, n_steps, n_warm, prefetch=pinned)  # device time, max over ranks
+        loss = trainer.mean_loss()
+        del trainer, model, batches
+        torch.cuda.empty_cache()
+        return secs, loss, nparam
+
+    secs, loss, nparam = run("b200", steps, warmup)
+    out = {
+        "config": f"BASELINE.json configs[2]: Mask2Former Swin-T fine-tune, synthetic {height}x{width}, {classes} classes, "
+                  f"batch {batch} per GPU, fp32, AdamW, gradient accumulation {GRADIENT_ACCUMULATION}",
+        "impl": "weed_instance_segmentation_b200.train.Trainer (MSDeformAttn modules + batched loss + pinned uint8 input)",
+        "images_per_s": world * batch * steps / secs, "ms_per_step": secs / steps * 1e3, "micro_batches_timed": steps,
+        "warmup": warmup, "n_gpus": world, "loss": loss,
+        # one bucketed all-reduce of every gradient per optimizer step (every GRADIENT_ACCUMULATION micro-batches)
+        "allreduce_bytes": nparam * 4 if world > 1 else 0, "allreduce_every_micro_batches": GRADIENT_ACCUMULATION,
+        "params": nparam, "backend": "nccl" if world > 1 else None,
+    }
+    if with_stock and world == 1:
+        s2, l2, _ = run("reference", steps, 3)
+        out["stock_hf"] = {"images_per_s": batch * steps / s2, "ms_per_step": s2 / steps * 1e3, "loss": l2,
+                           "what": "unmodified transformers Mask2FormerForUniversalSegmentation, same batches and step"}
+    return out
+
+
 def inference_throughput(model, device, args, rank: int) -> float:
     """Seconds for ``args.steps`` forward passes on one replica (max over ranks when run under torchrun)."""
     model = model.to(device).eval()
