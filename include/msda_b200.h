@@ -208,6 +208,24 @@ int msda_b200_point_sample_backward(float* const* grad_planes /*dev, R*/, const 
                                     int32_t K, void* stream);
 
 /*
+ * Pixel-decoder input assembly (M2F:1301-1313): GroupNorm of a 1x1-conv output
+ * x (B, C, HW; NCHW with the spatial dims flattened; float32 or bfloat16) fused with the flatten / transpose / concat
+ * that feeds the encoder:   out[b, p, c] = (x[b, c, p] - mean[b, g]) * rstd[b, g] * gamma[c] + beta[c],   g = c / (C/G),
+ * float32, written into rows of a (B, S, C) tensor: `out` points at the first row of this level and consecutive batch
+ * items are `out_batch_stride` ELEMENTS apart (S * C), so the three levels land side by side without a concat copy.
+ * stats (B * G * 2 float32) receives (mean, rstd) for the backward.  C / G <= 8 (GroupNorm(32, 256)).
+ * Backward: grad_x (dtype of x, NCHW) from grad_out (the same rows, float32); grad_gamma / grad_beta (C float32) are
+ * ACCUMULATED (the caller zero-fills them once for all levels); scratch: B * G * 2 float32.
+ */
+int msda_b200_groupnorm_to_rows_forward(const void* x /*dev*/, int x_dtype, const float* gamma /*dev*/,
+                                        const float* beta /*dev*/, float eps, float* out /*dev*/, int64_t out_batch_stride,
+                                        float* stats /*dev*/, int64_t B, int32_t C, int64_t HW, int32_t G, void* stream);
+int msda_b200_groupnorm_to_rows_backward(const float* grad_out /*dev*/, int64_t grad_out_batch_stride, const void* x /*dev*/,
+                                         int x_dtype, const float* gamma /*dev*/, const float* stats /*dev*/,
+                                         void* grad_x /*dev*/, float* grad_gamma /*dev*/, float* grad_beta /*dev*/,
+                                         float* scratch /*dev*/, int64_t B, int32_t C, int64_t HW, int32_t G, void* stream);
+
+/*
  * Host-buffer pipeline: the op with every tensor in HOST memory (the boundary a caller without device
  * buffers binds; bench.py's `e2e` leg).  The batch is cut into chunks of `chunk_images` images; each chunk
  * is copied to a device staging slot, run through msda_b200_forward (+ msda_b200_backward) and its results

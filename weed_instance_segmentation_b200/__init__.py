@@ -15,11 +15,14 @@ from .fused import MSDeformAttnFusedFunction, ms_deform_attn_fused  # noqa: F401
 from . import criterion  # noqa: F401
 from .criterion import convert_criterion, restore_criterion  # noqa: F401
 from .host import HostPipeline  # noqa: F401
+from .pixel_decoder import convert_pixel_decoder_inputs, groupnorm_to_rows  # noqa: F401
 from .point_sample import point_sample  # noqa: F401
 from .hf_patch import install, installed, is_installed, uninstall  # noqa: F401
 
 __all__ = [
     "HostPipeline",
+    "convert_pixel_decoder_inputs",
+    "groupnorm_to_rows",
     "convert_criterion",
     "restore_criterion",
     "point_sample",

@@ -33,6 +33,8 @@ EXPORTS = (
     "msda_b200_add_layernorm_forward",
     "msda_b200_add_layernorm_backward",
     "msda_b200_column_sum",
+    "msda_b200_groupnorm_to_rows_forward",
+    "msda_b200_groupnorm_to_rows_backward",
     "msda_b200_point_sample_forward",
     "msda_b200_point_sample_backward",
     "msda_b200_host_pipeline_create",
@@ -105,6 +107,12 @@ def load() -> ctypes.CDLL:
                                                      ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_groupnorm_to_rows_forward.restype = ctypes.c_int
+    lib.msda_b200_groupnorm_to_rows_forward.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_float, vp, ctypes.c_int64, vp,
+                                                        ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_groupnorm_to_rows_backward.restype = ctypes.c_int
+    lib.msda_b200_groupnorm_to_rows_backward.argtypes = [vp, ctypes.c_int64, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp,
+                                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_point_sample_forward.restype = ctypes.c_int
     lib.msda_b200_point_sample_forward.argtypes = [vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_point_sample_backward.restype = ctypes.c_int

@@ -61,6 +61,8 @@ def use_b200_path(model, mode: str = "modules", criterion: bool = True) -> None:
     hf_patch.install()
     if mode == "modules":
         modules.convert_pixel_decoder(model)
+        from .pixel_decoder import convert_pixel_decoder_inputs
+        convert_pixel_decoder_inputs(model)  # input assembly: GroupNorm + transpose + concat kernels, cached embeddings
         if criterion and hasattr(model, "criterion"):
             from .criterion import convert_criterion
             convert_criterion(model)
