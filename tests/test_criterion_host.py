@@ -152,3 +152,14 @@ def test_batch_without_any_target_matches_reference():
     out, gm, gc = run(mine, masks, classes, mask_labels, class_labels, seed=1)
     assert out["loss_mask"].item() == 0.0 and out["loss_dice"].item() == 0.0 and out["loss_cross_entropy"].item() > 0
     assert all(g is None or g.abs().max().item() == 0.0 for g in gm) and all(g.abs().max().item() > 0 for g in gc)
+
+
+def test_mixed_size_targets_are_refused():
+    """The reference pads targets to the largest size of the batch before sampling (M2F:612); the batched criterion
+    samples planes in place, so it refuses such a batch instead of silently sampling other points."""
+    from weed_instance_segmentation_b200.criterion import convert_criterion
+    loss, masks, classes, mask_labels, class_labels = make_problem(3)
+    mask_labels[1] = mask_labels[1][:, :-8, :-4].contiguous()
+    mine = convert_criterion(copy.deepcopy(loss), sampler=grid_sample_sampler)
+    with pytest.raises(ValueError, match="different sizes"):
+        run(mine, masks, classes, mask_labels, class_labels, seed=1)

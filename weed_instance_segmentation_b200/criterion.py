@@ -69,6 +69,11 @@ def _criterion_forward(self, masks_queries_logits, class_queries_logits, mask_la
         targets = [t if t.dtype in (torch.float32, torch.bfloat16, torch.uint8, torch.bool) else t.float()
                    for t in mask_labels]                                             # binary masks may stay 1 byte/pixel
         targets = [t.reshape(-1, *t.shape[-2:]) for t in targets]
+        if len({tuple(t.shape[-2:]) for t in targets}) > 1:
+            # the reference pads all targets to the largest size of the batch first (M2F:612) and samples the PADDED
+            # extent; sampling every plane at its own extent would silently give other point labels
+            raise ValueError("mask_labels of different sizes in one batch are not supported by the batched criterion "
+                             "(the reference's collate stacks equally sized images, dataset_utils.py:45-53)")
         sources = preds + targets
 
         # ---- 2. matcher costs of every (layer, image) at once (M2F:440-470)

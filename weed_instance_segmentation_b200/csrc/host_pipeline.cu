@@ -53,6 +53,7 @@ struct msda_b200_host_pipeline {
   cudaStream_t s_h2d[kCopyLanes] = {}, s_comp = nullptr, s_d2h[kCopyLanes] = {};
   cudaEvent_t fork = nullptr, tail[kCopyLanes] = {};
   uint64_t next = 0;  // chunks enqueued so far (slot = next % nslots)
+  bool poisoned = false;  // a step failed half way: its batch is incomplete, further steps are refused
 };
 
 namespace {
@@ -106,6 +107,9 @@ extern "C" int msda_b200_host_pipeline_create(const msda_b200_desc* desc, int32_
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "host_pipeline_create: chunk_images >= 1 and 2 <= slots <= 16");
   if (desc->B < 1 || desc->L < 1 || !desc->spatial_shapes_hw || !desc->level_start_index)
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "host_pipeline_create: incomplete descriptor");
+  // The library's own descriptor checks FIRST (L <= MSDA_B200_MAX_LEVELS, positive sizes, level table inside S):
+  // only a validated descriptor says how many entries of the caller's arrays may be read.
+  if (int rc = msda_b200_internal_validate(desc)) return rc;  // last_error set by validate
   msda_b200_host_pipeline* p = new (std::nothrow) msda_b200_host_pipeline();
   if (!p) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "host_pipeline_create: out of host memory");
   p->desc = *desc;
@@ -176,6 +180,8 @@ extern "C" int msda_b200_host_pipeline_step(msda_b200_host_pipeline* p, const vo
                                             void* grad_value, float* grad_sampling_loc, void* grad_attn_weight,
                                             void* stream) {
   if (!p) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "host_pipeline_step: NULL pipeline");
+  if (p->poisoned)
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "host_pipeline_step: an earlier step failed; destroy the pipeline");
   const bool bw = p->with_backward != 0;
   if (!value || !sampling_loc || !attn_weight || !output ||
       (bw && (!grad_output || !grad_value || !grad_sampling_loc || !grad_attn_weight)))
@@ -211,13 +217,18 @@ extern "C" int msda_b200_host_pipeline_step(msda_b200_host_pipeline* p, const vo
     cd.B = nb;
     int rc = msda_b200_forward(&cd, s.in + p->in_off[0], reinterpret_cast<const float*>(s.in + p->in_off[1]),
                                s.in + p->in_off[2], s.out + p->out_off[0], p->query_order, p->s_comp);
-    if (rc != MSDA_B200_OK) return rc;
-    if (bw) {
+    if (rc == MSDA_B200_OK && bw)
       rc = msda_b200_backward(&cd, s.in + p->in_off[0], reinterpret_cast<const float*>(s.in + p->in_off[1]),
                               s.in + p->in_off[2], s.in + p->in_off[3], s.out + p->out_off[1],
                               reinterpret_cast<float*>(s.out + p->out_off[2]), s.out + p->out_off[3], s.ws,
                               p->ws_bytes, p->query_order, p->s_comp);
-      if (rc != MSDA_B200_OK) return rc;
+    if (rc != MSDA_B200_OK) {
+      // keep the slot's event chain intact (later waits must not see a stale comp_done / out_done) and refuse
+      // further steps: part of this batch never ran
+      cudaEventRecord(s.comp_done, p->s_comp);
+      cudaEventRecord(s.out_done, s_out);
+      p->poisoned = true;
+      return rc;
     }
     HP_CUDA(cudaEventRecord(s.comp_done, p->s_comp));
     // D2H

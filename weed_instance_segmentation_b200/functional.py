@@ -18,6 +18,7 @@ Error behaviour mirrors the reference module (M2F:942-945, :978): shape mismatch
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Sequence
 
 import torch
@@ -45,7 +46,7 @@ _BWD_V1 = os.environ.get("MSDA_B200_BWD_V1", "0") == "1"
 _STRICT_PADDING = os.environ.get("MSDA_B200_STRICT_PADDING", "0") == "1"
 
 _order_cache: dict = {}
-_lsi_checked: set = set()
+_lsi_checked: dict = {}
 
 
 def _shapes_list(value_spatial_shapes) -> list[tuple[int, int]]:
@@ -58,9 +59,8 @@ def _shapes_list(value_spatial_shapes) -> list[tuple[int, int]]:
 def _level_start(shapes: Sequence[tuple[int, int]], level_start_index) -> list[int]:
     """Host copy of ``level_start_index`` (M2F:1321).
 
-    HF threads a CUDA tensor through every layer but the reference op never reads it. Reading it
-    back would cost a device sync per call, so a CUDA tensor is compared with the prefix sum of
-    the shapes once per shape set and the derived values are used from then on.
+    HF threads a CUDA tensor through every layer but the reference op never reads it. Reading it back costs a device
+    sync, so the host copy is remembered per tensor object (the same tensor reaches all six layers of a forward).
     """
     derived, acc = [], 0
     for h, w in shapes:
@@ -70,13 +70,18 @@ def _level_start(shapes: Sequence[tuple[int, int]], level_start_index) -> list[i
         return derived
     if isinstance(level_start_index, torch.Tensor):
         if level_start_index.is_cuda:
-            key = (tuple(shapes), level_start_index.data_ptr())
-            if key not in _lsi_checked:
-                given = [int(v) for v in level_start_index.tolist()]
-                if given != derived:
-                    return given  # unusual layout: honour it (costs the sync every call)
-                _lsi_checked.add(key)
-            return derived
+            # keyed on the tensor OBJECT and its version counter (not on data_ptr: the caching allocator hands the same
+            # address to later tensors with other contents); HF builds a fresh tensor per forward, so in practice this
+            # costs one small D2H read per forward of the model, not per layer
+            key = (tuple(shapes), id(level_start_index), level_start_index._version)
+            hit = _lsi_checked.get(key)
+            if hit is not None and hit[0]() is level_start_index:
+                return hit[1]
+            given = [int(v) for v in level_start_index.tolist()]
+            if len(_lsi_checked) > 64:
+                _lsi_checked.clear()
+            _lsi_checked[key] = (weakref.ref(level_start_index), given)
+            return given
         return [int(v) for v in level_start_index.tolist()]
     return [int(v) for v in level_start_index]
 
