@@ -8,7 +8,9 @@ Compares, with identical weights and inputs:
   modules   : modules.EncoderLayer + MSDeformAttn, un-fused prologue
   fused     : modules.EncoderLayer + MSDeformAttn with the fused softmax/location prologue
   fused+norm: the same plus the fused residual + LayerNorm kernels (layer_norm.py)
-  fused+norm+linear: the same plus projections with the fused bias-gradient reduction (linear.py)
+  fused+norm+linear: the same plus projections with the fused bias-gradient reduction (linear.py), fc1 with bias + ReLU in
+              the GEMM epilogue, and the bfloat16 copy of the first LayerNorm's output feeding fc1 (no cast kernel)
+  full      : the same plus reference points computed inside the kernels (no reference-point tensor)
 
     python bench_layer.py [--amp bf16|none] [--steps K] [--warmup W] [--batch B]
 Prints one JSON line.
@@ -63,12 +65,13 @@ def main():
 
     def variant(name):
         layer = copy.deepcopy(ref_layer)
-        if name in ("modules", "fused", "fused+norm", "fused+norm+linear"):
+        if name in ("modules", "fused", "fused+norm", "fused+norm+linear", "full"):
             layer = modules.EncoderLayer.from_hf(layer)
             layer.self_attn.assume_no_padding = True
             layer.self_attn.fused_prologue = name != "modules"
-            layer.fused_norm = name in ("fused+norm", "fused+norm+linear")
-            layer.fused_linear = layer.self_attn.fused_linear = name == "fused+norm+linear"
+            layer.fused_norm = name in ("fused+norm", "fused+norm+linear", "full")
+            layer.fused_linear = layer.self_attn.fused_linear = name in ("fused+norm+linear", "full")
+            layer.self_attn.implicit_reference_points = name == "full"
         return layer
 
     def run(layer, patched):
@@ -104,13 +107,13 @@ def main():
 
     results, outs = {}, {}
     for name, patched in (("reference", False), ("function", True), ("modules", True), ("fused", True), ("fused+norm", True),
-                          ("fused+norm+linear", True)):
+                          ("fused+norm+linear", True), ("full", True)):
         ms, out, gx = run(variant(name), patched)
         results[name] = {"ms_per_layer_fwd_bwd": ms}
         outs[name] = (out, gx)
         torch.cuda.empty_cache()
     r_out, r_gx = outs["reference"]
-    for name in ("function", "modules", "fused", "fused+norm", "fused+norm+linear"):
+    for name in ("function", "modules", "fused", "fused+norm", "fused+norm+linear", "full"):
         o, g = outs[name]
         results[name]["out_rel_err_vs_reference"] = ((o - r_out).abs().max() / r_out.abs().max()).item()
         results[name]["grad_input_rel_err_vs_reference"] = ((g - r_gx).abs().max() / r_gx.abs().max()).item()

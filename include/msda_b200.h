@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 6
+#define MSDA_B200_ABI_VERSION 7
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -162,17 +162,20 @@ int msda_b200_backward_fused(const msda_b200_desc* desc, const void* value /*dev
  * gamma, beta and every gradient are float32.  grad_sum is d loss / d (x + residual), i.e. the gradient of both
  * inputs; grad_sum_lowp (optional) receives the same values in bfloat16 for a bfloat16 x.  The library zero-fills
  * grad_gamma / grad_beta before accumulating.
+ * y_lowp (optional): the same y rounded to bfloat16 -- the operand of the projection that follows under autocast
+ * (fc1 after the first LayerNorm, M2F:1052), so no separate cast kernel runs; grad_y_lowp (optional) is the gradient
+ * that came back through that copy and is added to grad_y inside the backward kernel.
  */
 int msda_b200_add_layernorm_forward(const void* x /*dev*/, int x_dtype, const void* residual /*dev*/, int residual_dtype,
                                     const float* gamma /*dev*/, const float* beta /*dev*/, float eps, float* y /*dev*/,
-                                    float* mean /*dev, rows*/, float* rstd /*dev, rows*/, int64_t rows, int32_t channels,
-                                    void* stream);
+                                    void* y_lowp /*dev|NULL, bfloat16*/, float* mean /*dev, rows*/, float* rstd /*dev, rows*/,
+                                    int64_t rows, int32_t channels, void* stream);
 
-int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* x /*dev*/, int x_dtype,
-                                     const void* residual /*dev*/, int residual_dtype, const float* gamma /*dev*/,
-                                     const float* mean /*dev*/, const float* rstd /*dev*/, float* grad_sum /*dev*/,
-                                     void* grad_sum_lowp /*dev|NULL*/, float* grad_gamma /*dev*/, float* grad_beta /*dev*/,
-                                     int64_t rows, int32_t channels, void* stream);
+int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* grad_y_lowp /*dev|NULL, bfloat16*/,
+                                     const void* x /*dev*/, int x_dtype, const void* residual /*dev*/, int residual_dtype,
+                                     const float* gamma /*dev*/, const float* mean /*dev*/, const float* rstd /*dev*/,
+                                     float* grad_sum /*dev*/, void* grad_sum_lowp /*dev|NULL*/, float* grad_gamma /*dev*/,
+                                     float* grad_beta /*dev*/, int64_t rows, int32_t channels, void* stream);
 
 /*
  * Column sum of a contiguous (rows x cols) matrix into float32 -- the bias gradient of a projection

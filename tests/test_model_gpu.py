@@ -93,7 +93,7 @@ def test_instance_masks_unchanged(models):
     from weed_instance_segmentation_b200 import synth
     ref, fn, _, _ = models
     proc = Mask2FormerImageProcessor()
-    ious = []
+    ious, differing, explained = [], 0, 0
     for seed in range(3):
         batch = synth.collate_batch(2, 128, 160, num_classes=3, max_instances=4, seed=20 + seed, device="cuda")
         with torch.no_grad():
@@ -104,17 +104,43 @@ def test_instance_masks_unchanged(models):
         kw = dict(threshold=0.0, mask_threshold=0.5, target_sizes=batch["target_sizes"])
         p_ref = proc.post_process_instance_segmentation(o_ref, **kw)
         p_new = proc.post_process_instance_segmentation(o_b200, **kw)
-        for a, b in zip(p_ref, p_new):
+        # pixels where ANY query's mask logit (upsampled as the post-processing does, M2FIP:605-725) sits within
+        # 1e-4 of the largest logit magnitude from the 0.5-probability threshold: only those may change owner
+        logits = o_ref.masks_queries_logits
+        tol = 1e-4 * logits.abs().max().item()
+        for i, (a, b) in enumerate(zip(p_ref, p_new)):
             sa, sb = a["segmentation"], b["segmentation"]
-            ids = [int(i) for i in sa.unique().tolist() if i >= 0]
+            up = torch.nn.functional.interpolate(logits[i][None], size=tuple(sa.shape), mode="bilinear",
+                                                 align_corners=False)[0]
+            ambiguous = (up.abs() < tol).any(0).to(sa.device)
+            diff = sa != sb
+            differing += int(diff.sum())
+            explained += int((diff & ambiguous).sum())
+            ids = [int(k) for k in sa.unique().tolist() if k >= 0]
             assert len(a["segments_info"]) == len(b["segments_info"])
-            for i in ids:
-                ma, mb = sa == i, sb == i
+            for k in ids:
+                ma, mb = (sa == k) & ~ambiguous, (sb == k) & ~ambiguous
                 ious.append((ma & mb).sum().item() / max((ma | mb).sum().item(), 1))
     assert ious, "no instances produced; lower the threshold"
-    # fp32 logits of the two models differ by ~1e-5 relative, which can move a pixel whose mask logit sits
-    # within that distance of the 0.5 threshold (one pixel of a 39-pixel random-init mask was observed)
-    assert sum(ious) / len(ious) >= 0.995 and min(ious) >= 0.95, (min(ious), sum(ious) / len(ious))
+    # per-instance mask IoU is exactly 1 outside the threshold-ambiguous pixels, and every differing pixel is one of them
+    assert differing == explained, (differing, explained)
+    assert min(ious) == 1.0, (min(ious), sum(ious) / len(ious))
+
+
+def test_config1_geometry_swin_t_inference_matches(models):
+    """BASELINE.json configs[0] geometry: the full-size Swin-T model, batch 1, 512x512, fp32 -- stock model vs the B200
+    operator installed (M2F:980 rebound), same weights."""
+    import weed_instance_segmentation_b200 as wis
+    from weed_instance_segmentation_b200 import train
+    model = train.build_model("swin_t", num_labels=3, seed=0).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    pixel_values = torch.randn(1, 3, 512, 512, generator=g, device="cuda")
+    with torch.no_grad():
+        want = model(pixel_values=pixel_values)
+        with wis.installed():
+            got = model(pixel_values=pixel_values)
+    assert _rel(got.masks_queries_logits, want.masks_queries_logits) < 5e-4
+    assert _rel(got.class_queries_logits, want.class_queries_logits) < 5e-4
 
 
 def test_bf16_autocast_forward_close(models):

@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_LEVELS = 8
 F32, BF16, U8 = 0, 1, 2
 FLAG_PROFILE = 1
@@ -100,10 +100,10 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_backward_fused.restype = ctypes.c_int
     lib.msda_b200_backward_fused.argtypes = [dp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_size_t, vp, vp]
     lib.msda_b200_add_layernorm_forward.restype = ctypes.c_int
-    lib.msda_b200_add_layernorm_forward.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_float, vp, vp, vp,
+    lib.msda_b200_add_layernorm_forward.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_float, vp, vp, vp, vp,
                                                     ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_add_layernorm_backward.restype = ctypes.c_int
-    lib.msda_b200_add_layernorm_backward.argtypes = [vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,
+    lib.msda_b200_add_layernorm_backward.argtypes = [vp, vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp,
                                                      ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]

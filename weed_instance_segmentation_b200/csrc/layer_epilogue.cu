@@ -57,7 +57,8 @@ template <typename XT, typename RT, int CH>
 __global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ r,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, float eps,
-                                                                     float* __restrict__ y, float* __restrict__ mean_out,
+                                                                     float* __restrict__ y, void* __restrict__ y_lowp,
+                                                                     float* __restrict__ mean_out,
                                                                      float* __restrict__ rstd_out, long long N) {
   constexpr int C = CH * 128;
   const int lane = threadIdx.x & 31;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void*
     o.z = (s[k].z - mean) * rstd * g.z + bt.z;
     o.w = (s[k].w - mean) * rstd * g.w + bt.w;
     reinterpret_cast<float4*>(y)[row * (C / 4) + c4] = o;
+    if (y_lowp) store4_bf16(y_lowp, row * (C / 4) + c4, o);  // the next projection's bf16 operand, no separate cast
   }
   if (lane == 0) {
     mean_out[row] = mean;
@@ -98,7 +100,9 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void*
 }
 
 template <typename XT, typename RT, int CH, bool LOWP>
-__global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x,
+__global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float* __restrict__ dy,
+                                                                     const void* __restrict__ dy_lowp,
+                                                                     const void* __restrict__ x,
                                                                      const void* __restrict__ r,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ mean_in,
@@ -123,7 +127,11 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float
       const int c4 = k * 32 + lane;
       const long long i4 = row * (C / 4) + c4;
       const float4 a = load4<XT>(x, i4), b = load4<RT>(r, i4);
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + i4);
+      float4 d = __ldg(reinterpret_cast<const float4*>(dy) + i4);
+      if (dy_lowp) {  // gradient that arrived through the bf16 copy of y (the projection fed from it)
+        const float4 e = load4<__nv_bfloat16>(dy_lowp, i4);
+        d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+      }
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
       xh[k] = make_float4((a.x + b.x - mean) * rstd, (a.y + b.y - mean) * rstd, (a.z + b.z - mean) * rstd,
                           (a.w + b.w - mean) * rstd);
@@ -170,23 +178,24 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float
 
 template <int CH>
 int launch_fwd_ch(int xd, int rd, const void* x, const void* r, const float* gamma, const float* beta, float eps, float* y,
-                  float* mean, float* rstd, long long N, cudaStream_t st) {
+                  void* y_lowp, float* mean, float* rstd, long long N, cudaStream_t st) {
   const unsigned blocks = (unsigned)((N + kRowsPerBlock - 1) / kRowsPerBlock);
   using bf = __nv_bfloat16;
   if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32)
-    add_layernorm_fwd_kernel<bf, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+    add_layernorm_fwd_kernel<bf, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
   else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32)
-    add_layernorm_fwd_kernel<float, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+    add_layernorm_fwd_kernel<float, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
   else if (xd == MSDA_B200_BF16 && rd == MSDA_B200_BF16)
-    add_layernorm_fwd_kernel<bf, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+    add_layernorm_fwd_kernel<bf, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
   else
-    add_layernorm_fwd_kernel<float, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, mean, rstd, N);
+    add_layernorm_fwd_kernel<float, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
 }
 
 template <int CH>
-int launch_bwd_ch(int xd, int rd, const float* dy, const void* x, const void* r, const float* gamma, const float* mean,
+int launch_bwd_ch(int xd, int rd, const float* dy, const void* dy_lowp, const void* x, const void* r, const float* gamma,
+                  const float* mean,
                   const float* rstd, float* ds, void* ds_lowp, float* dgamma, float* dbeta, long long N, cudaStream_t st) {
   // ~4 blocks per SM; each block walks a contiguous range of rows so the gamma/beta partials stay in registers
   long long blocks = 148 * 4;
@@ -198,10 +207,10 @@ int launch_bwd_ch(int xd, int rd, const float* dy, const void* x, const void* r,
   do {                                                                                                            \
     if (ds_lowp)                                                                                                  \
       add_layernorm_bwd_kernel<XT, RT, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(                          \
-          dy, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                            \
+          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                   \
     else                                                                                                          \
       add_layernorm_bwd_kernel<XT, RT, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(                         \
-          dy, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                            \
+          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                   \
   } while (0)
   if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32) MSDA_LN_BWD(bf, float);
   else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32) MSDA_LN_BWD(float, float);
@@ -219,7 +228,7 @@ bool bad_dtype(int d) { return d != MSDA_B200_F32 && d != MSDA_B200_BF16; }
 extern "C" {
 
 int msda_b200_add_layernorm_forward(const void* x, int x_dtype, const void* residual, int residual_dtype,
-                                    const float* gamma, const float* beta, float eps, float* y, float* mean,
+                                    const float* gamma, const float* beta, float eps, float* y, void* y_lowp, float* mean,
                                     float* rstd, int64_t rows, int32_t channels, void* stream) {
   if (rows < 0 || channels <= 0 || channels % 128 != 0 || channels > kMaxC)
     return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: channels must be a multiple of 128, at most 512");
@@ -230,14 +239,14 @@ int msda_b200_add_layernorm_forward(const void* x, int x_dtype, const void* resi
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_forward: NULL tensor pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (channels / 128) {
-    case 1: return launch_fwd_ch<1>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
-    case 2: return launch_fwd_ch<2>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
-    case 4: return launch_fwd_ch<4>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, mean, rstd, rows, st);
+    case 1: return launch_fwd_ch<1>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
+    case 2: return launch_fwd_ch<2>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
+    case 4: return launch_fwd_ch<4>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
   }
   return MSDA_B200_ERR_UNSUPPORTED;
 }
 
-int msda_b200_add_layernorm_backward(const float* grad_y, const void* x, int x_dtype, const void* residual,
+int msda_b200_add_layernorm_backward(const float* grad_y, const void* grad_y_lowp, const void* x, int x_dtype, const void* residual,
                                      int residual_dtype, const float* gamma, const float* mean, const float* rstd,
                                      float* grad_sum, void* grad_sum_lowp, float* grad_gamma, float* grad_beta,
                                      int64_t rows, int32_t channels, void* stream) {
@@ -254,9 +263,9 @@ int msda_b200_add_layernorm_backward(const float* grad_y, const void* x, int x_d
   if (!grad_y || !x || !residual || !gamma || !mean || !rstd || !grad_sum)
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_backward: NULL tensor pointer");
   switch (channels / 128) {
-    case 1: return launch_bwd_ch<1>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
-    case 2: return launch_bwd_ch<2>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
-    case 4: return launch_bwd_ch<4>(x_dtype, residual_dtype, grad_y, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 1: return launch_bwd_ch<1>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 2: return launch_bwd_ch<2>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 4: return launch_bwd_ch<4>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
   }
   return MSDA_B200_ERR_UNSUPPORTED;
 }

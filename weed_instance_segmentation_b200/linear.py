@@ -57,6 +57,54 @@ class LinearFunction(torch.autograd.Function):
         return grad_x, grad_w, grad_b
 
 
+class LinearReLUFunction(torch.autograd.Function):
+    """``relu(F.linear(x, weight, bias))`` with bias + ReLU in the GEMM epilogue (cuBLASLt through
+    ``torch._addmm_activation``; the GEMM stays a library call, M2F:1052-1053) and the bias gradient from the B200
+    column-sum kernel."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias):
+        if torch.is_autocast_enabled("cuda"):
+            dt = torch.get_autocast_dtype("cuda")
+            xc, wc, bc = x.to(dt), weight.to(dt), bias.to(dt)
+        else:
+            xc, wc, bc = x, weight, bias
+        with torch.autocast("cuda", enabled=False):
+            y = torch._addmm_activation(bc, xc.reshape(-1, xc.shape[-1]), wc.t(), use_gelu=False)
+        y = y.reshape(*xc.shape[:-1], wc.shape[0])
+        ctx.save_for_backward(xc, wc, y)
+        ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_y):
+        xc, wc, y = ctx.saved_tensors
+        xd, wd, bd = ctx.in_dtypes
+        gy = torch.ops.aten.threshold_backward(grad_y.to(y.dtype).contiguous(), y, 0)  # relu'
+        g2 = gy.reshape(-1, gy.shape[-1])
+        need_x, need_w, need_b = ctx.needs_input_grad
+        grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
+        grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
+        grad_b = column_sum(g2).to(bd) if need_b else None
+        return grad_x, grad_w, grad_b
+
+
+def _kernel_ok(x, weight, bias) -> bool:
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    C = weight.shape[0]
+    return (x.is_cuda and bias is not None and dt in _DTYPE_CODE and C % (8 if dt == torch.bfloat16 else 4) == 0
+            and C <= (2048 if dt == torch.bfloat16 else 1024))
+
+
+def linear_relu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """``relu(F.linear(x, weight, bias))``, bias and ReLU in the GEMM epilogue (see :class:`LinearReLUFunction`)."""
+    if not _kernel_ok(x, weight, bias):
+        return F.relu(F.linear(x, weight, bias))
+    return LinearReLUFunction.apply(x, weight, bias)
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """``F.linear(x, weight, bias)`` whose backward reduces the bias gradient with the B200 kernel.
 

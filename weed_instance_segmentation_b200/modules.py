@@ -24,6 +24,7 @@ from .functional import ms_deform_attn
 from .fused import ms_deform_attn_fused
 from .layer_norm import add_layer_norm
 from .linear import linear as _fused_linear
+from .linear import linear_relu as _fused_linear_relu
 
 
 class MSDeformAttn(nn.Module):
@@ -100,6 +101,9 @@ class MSDeformAttn(nn.Module):
             )
         H, L, P = self.n_heads, self.n_levels, self.n_points
 
+        if torch.is_autocast_enabled("cuda") and hidden_states.is_cuda and hidden_states.dtype == torch.float32:
+            # both query projections read `hidden_states`: cast it to the autocast dtype ONCE (F.linear would do it twice)
+            hidden_states = hidden_states.to(torch.get_autocast_dtype("cuda"))
         value = self._proj(self.value_proj, encoder_hidden_states)
         if attention_mask is not None and not self.assume_no_padding:
             value = value.masked_fill(attention_mask[..., None], float(0))
@@ -177,14 +181,18 @@ class EncoderLayer(nn.Module):
     def _proj(self, layer: nn.Linear, x):
         return _fused_linear(x, layer.weight, layer.bias) if self.fused_linear else layer(x)
 
-    def _add_norm(self, branch, residual, norm):
-        """``norm(residual + branch)`` (M2F:1049-1050, 1058-1059); one fused kernel when ``fused_norm`` is set."""
+    def _add_norm(self, branch, residual, norm, also_lowp=False):
+        """``norm(residual + branch)`` (M2F:1049-1050, 1058-1059); one fused kernel when ``fused_norm`` is set.
+        ``also_lowp``: return ``(y, y_bf16_or_None)`` -- the bfloat16 copy comes out of the same kernel."""
         ok = (self.fused_norm and branch.is_cuda and branch.shape[-1] % 128 == 0 and branch.shape[-1] <= 512
               and branch.dtype in (torch.float32, torch.bfloat16) and residual.dtype in (torch.float32, torch.bfloat16)
               and (torch.is_autocast_enabled() or (branch.dtype == residual.dtype == torch.float32)))
         if ok:
-            return add_layer_norm(branch, residual, norm.weight, norm.bias, norm.eps)
-        return norm(residual + branch)
+            lowp = also_lowp and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            res = add_layer_norm(branch, residual, norm.weight, norm.bias, norm.eps, also_lowp=lowp)
+            return (res if lowp else (res, None)) if also_lowp else res
+        y = norm(residual + branch)
+        return (y, None) if also_lowp else y
 
     def forward(
         self,
@@ -209,10 +217,15 @@ class EncoderLayer(nn.Module):
             output_attentions=output_attentions,
         )
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
-        hidden_states = self._add_norm(hidden_states, residual, self.self_attn_layer_norm)
+        # the first LayerNorm also emits its output in bfloat16 (under autocast): fc1 reads that copy, no cast kernel
+        hidden_states, lowp = self._add_norm(hidden_states, residual, self.self_attn_layer_norm, also_lowp=True)
 
         residual = hidden_states
-        hidden_states = self.activation_fn(self._proj(self.fc1, hidden_states))
+        fc1_in = lowp if lowp is not None else hidden_states
+        if self.fused_linear and self.activation_fn is F.relu:
+            hidden_states = _fused_linear_relu(fc1_in, self.fc1.weight, self.fc1.bias)  # bias + ReLU in the GEMM epilogue
+        else:
+            hidden_states = self.activation_fn(self._proj(self.fc1, fc1_in))
         hidden_states = F.dropout(hidden_states, p=self.activation_dropout, training=self.training)
         hidden_states = self._proj(self.fc2, hidden_states)
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
