@@ -66,6 +66,8 @@ extern "C" {
                                          /* bf16x2 atomics in place (no fp32 workspace, lossy)   */
 #define MSDA_B200_FLAG_BWD_V1 4u         /* backward: force the per-corner reduction kernel (v1)  */
                                          /* instead of the pixel-sorted kernel (v2, D=32 & P=4)  */
+#define MSDA_B200_FLAG_BWD_V2 32u        /* backward: force the CUDA-core pixel-sorted kernel (v2) instead of the  */
+                                         /* group-sorted tensor-core kernel (v3, bf16 values, D=32 & P=4)          */
 #define MSDA_B200_FLAG_NO_WINDOW 8u      /* never use the window-staged (TMA) kernels of msda_win.cu */
 #define MSDA_B200_FLAG_STRICT_PADDING 16u /* forward: skip the FMA of every zero-weight corner, so a non-finite  */
                                          /* value in a pixel grid_sample's zeros padding never reads (M2F:823)  */

@@ -19,6 +19,7 @@ FLAG_BF16_ATOMICS = 2
 FLAG_BWD_V1 = 4
 FLAG_NO_WINDOW = 8
 FLAG_STRICT_PADDING = 16
+FLAG_BWD_V2 = 32
 PROF_FWD, PROF_BWD_ZERO, PROF_BWD_MAIN, PROF_BWD_CONVERT = 0, 1, 2, 3
 
 # every symbol include/msda_b200.h declares

@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(NT) msda_bwd_kernel(const __grid_constant__ KP
 }
 
 #include "msda_bwd_sorted.cuh"
+#include "msda_bwd_mma.cuh"
 
 // fp32 accumulator -> bf16 grad_value, 8 elements per thread
 __global__ void __launch_bounds__(256) msda_cvt_f32_bf16_kernel(const float4* __restrict__ src, uint4* __restrict__ dst,
@@ -782,10 +783,34 @@ int launch_bwd_sorted_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   return check_launch("msda_b200_backward (sorted)");
 }
 
+// Backward v3 (msda_bwd_mma.cuh): group-sorted rows + mma.sync; same geometry as v2, fp32 accumulator only.
+constexpr int kMmaNT = 256, kMmaTQ = 128, kMmaGCAP = 256, kMmaRCAP = 1152;
+
+template <typename AT, bool FUSED>
+int launch_bwd_mma(const msda_b200_desc* d, KParams p, cudaStream_t st) {
+  constexpr int P = 4;
+  fill_geometry(d, p, kMmaTQ);
+  const size_t smem = mma_smem_layout<kMmaNT, kMmaTQ, P, kMmaGCAP, kMmaRCAP, FUSED>().total;
+  auto kern = msda_bwd_mma_kernel<AT, kMmaNT, kMmaTQ, P, kMmaGCAP, kMmaRCAP, FUSED>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
+  const long long blocks = (long long)p.B * p.num_tiles * p.H;
+  if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "backward: grid too large");
+  {
+    ProfScope ps((d->flags & MSDA_B200_FLAG_PROFILE) != 0, MSDA_B200_PROF_BWD_MAIN, st);
+    kern<<<(unsigned)blocks, kMmaNT, smem, st>>>(p);
+    ++g_launches;
+  }
+  return check_launch("msda_b200_backward (group-sorted, mma)");
+}
+
 template <typename VT, typename AT, int ACC, bool FUSED>
 int dispatch_bwd(const msda_b200_desc* d, const KParams& p, cudaStream_t st) {
   if constexpr (std::is_same<VT, __nv_bfloat16>::value) {
     if (sorted_applicable(d)) {
+      if constexpr (ACC == 0) {
+        if (!(d->flags & MSDA_B200_FLAG_BWD_V2)) return launch_bwd_mma<AT, FUSED>(d, p, st);
+      }
       return launch_bwd_sorted_cfg<VT, AT, ACC, FUSED, kSortNT, kSortTQ, 4>(d, p, st);
     }
   }

@@ -41,6 +41,7 @@ _TILE = _parse_tile(os.environ.get("MSDA_B200_TILE", "8x16"))
 _USE_ORDER = os.environ.get("MSDA_B200_QUERY_ORDER", "1") != "0"
 _BF16_ATOMICS = os.environ.get("MSDA_B200_BF16_ATOMICS", "0") == "1"
 _BWD_V1 = os.environ.get("MSDA_B200_BWD_V1", "0") == "1"
+_BWD_V2 = os.environ.get("MSDA_B200_BWD_V2", "0") == "1"  # CUDA-core pixel-sorted backward instead of the tensor-core one
 # Forward: never multiply a zero-weight corner (exact zeros padding even when `value` holds NaN / Inf in pixels no
 # sample reads; 25-30 % slower, see include/msda_b200.h MSDA_B200_FLAG_STRICT_PADDING).
 _STRICT_PADDING = os.environ.get("MSDA_B200_STRICT_PADDING", "0") == "1"
@@ -250,6 +251,8 @@ class MSDeformAttnFunction(torch.autograd.Function):
             flags |= _cabi.FLAG_BF16_ATOMICS
         if _BWD_V1:
             flags |= _cabi.FLAG_BWD_V1
+        if _BWD_V2:
+            flags |= _cabi.FLAG_BWD_V2
         desc, keep = _cabi.make_desc(B, S, Q, H, D, L, P, _DTYPE_CODE[value.dtype], _DTYPE_CODE[attn.dtype],
                                      shapes, level_start, flags)
         grad_value = torch.empty_like(value)
