@@ -784,7 +784,7 @@ int launch_bwd_sorted_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
 }
 
 // Backward v3 (msda_bwd_mma.cuh): group-sorted rows + mma.sync; same geometry as v2, fp32 accumulator only.
-constexpr int kMmaNT = 256, kMmaTQ = 128, kMmaGCAP = 256, kMmaRCAP = 1152;
+constexpr int kMmaNT = 256, kMmaTQ = 128, kMmaGCAP = 256, kMmaRCAP = 1024;
 
 template <typename AT, bool FUSED>
 int launch_bwd_mma(const msda_b200_desc* d, KParams p, cudaStream_t st) {

@@ -28,30 +28,46 @@
 // grad_out rows are staged ONCE per block with their 32 channels permuted so that (i) the m16n8k16 fragments of both
 // products come straight out of ldmatrix and (ii) every lane ends up holding 4 consecutive channels of a slot, i.e.
 // one 16-byte reduction.  Stored row = 4 chunks of 8 bf16; chunk j, element i holds channel 4*i + j; the chunk index
-// is XOR-swizzled with (row >> 1) & 3 so the eight 16-byte pieces of one ldmatrix tile spread over the banks.
+// is XOR-swizzled (go_swizzle) so the eight 16-byte pieces of one ldmatrix tile spread over the banks.
 //
 // Numerics: the dots are exact bf16 x bf16 products accumulated in fp32; the scatter uses slot weights rounded to
 // bf16 (relative 2^-9 per contribution, the same size as the bf16 rounding of grad_value itself).
 
 __device__ __forceinline__ void ldsm_x4(unsigned (&r)[4], unsigned addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+  asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void ldsm_x4_trans(unsigned (&r)[4], unsigned addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+  asm("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void ldsm_x2_trans(unsigned (&r)[2], unsigned addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
-               : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+  asm("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+// 8x8 b16 tile held one row per quad of lanes -> its transpose in the same layout (what ldmatrix.trans of the same
+// tile returns), without going back to shared memory
+__device__ __forceinline__ unsigned movm_trans(unsigned x) {
+  unsigned y;
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
 }
 // D (16x8, fp32) += A (16x16, bf16, row) * B (16x8, bf16, col)
 __device__ __forceinline__ void mma_bf16(float (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
                                          unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
-               "{%0, %1, %2, %3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+
+// XOR swizzle of the 16-byte chunk index of staged grad_out row `row`.  Eight list rows of one ldmatrix tile are mostly
+// queries of a small 2-D patch (row = 16*y + x inside the 8 x 16 query tile): bit 0 of x selects the upper / lower half
+// of the 128-byte bank line (64-byte rows), bit 1 of x and bit 0 of y go into the swizzle, so a 4 x 2 patch of queries
+// hits eight different 16-byte bank groups.
+__device__ __forceinline__ int go_swizzle(int row) { return ((row >> 1) & 1) | ((row >> 3) & 2); }
+
+#ifndef MSDA_MMA_MOVM
+#define MSDA_MMA_MOVM 1
+#endif
 
 struct MmaSmem {
   size_t w, go, wrow, dot, a, xy, cnt, item, id, fb, misc, stat, total;
@@ -71,8 +87,8 @@ __host__ __device__ inline MmaSmem mma_smem_layout() {
   s.a = o;    o += sizeof(float) * NS;
   s.xy = o;   o += sizeof(int) * NS;          // x | y << 12 | derivative codes << 24
   s.cnt = o;  o += sizeof(int) * GCAP;        // histogram, then fill cursors
-  s.item = o; o += sizeof(int) * (GCAP + RCAP / kMmaItemRows + 8);
-  s.id = o;   o += sizeof(unsigned short) * RCAP;
+  s.item = o; o += sizeof(uint2) * (GCAP + RCAP / kMmaItemRows + 8);  // (rows | n | slot mask, pixel offset)
+  s.id = o;   o += sizeof(unsigned) * RCAP;      // row code: staged grad_out row offset | sample | footprint position
   s.fb = o;   o += sizeof(unsigned short) * NS * 4;
   o = (o + 15) & ~size_t(15);
   s.misc = o; o += sizeof(int) * 64;
@@ -104,10 +120,10 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
   float* s_a = reinterpret_cast<float*>(smem_raw + lay.a);
   int* s_xy = reinterpret_cast<int*>(smem_raw + lay.xy);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + lay.cnt);
-  unsigned* s_item = reinterpret_cast<unsigned*>(smem_raw + lay.item);
-  unsigned short* s_id = reinterpret_cast<unsigned short*>(smem_raw + lay.id);
+  uint2* s_item = reinterpret_cast<uint2*>(smem_raw + lay.item);
+  unsigned* s_id = reinterpret_cast<unsigned*>(smem_raw + lay.id);
   unsigned short* s_fb = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
-  int* s_misc = reinterpret_cast<int*>(smem_raw + lay.misc);
+  int* const s_misc2 = reinterpret_cast<int*>(smem_raw + lay.misc);  // two sets of 32, alternating by level
   float* s_max = reinterpret_cast<float*>(smem_raw + lay.stat);
   float* s_inv = s_max + TQ;
   float* s_dsum = s_inv + TQ;
@@ -124,24 +140,6 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
   float* const acc_f = reinterpret_cast<float*>(p.grad_value_acc) + acc_base * 8;
   const unsigned go_sa = (unsigned)__cvta_generic_to_shared(s_go32);
   const unsigned wrow_sa = (unsigned)__cvta_generic_to_shared(s_wrow);
-
-  // grad_out rows of the tile, staged once: channel-permuted and chunk-swizzled (see the file header)
-  for (int i = tid; i < TQ * LPP; i += NT) {
-    const int ql = i >> 2, cc = i & 3;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (ql < nq) {
-      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
-      v = ldg16(reinterpret_cast<const uint4*>(p.grad_out) + (((long long)b * p.Q + q) * p.H + h) * LPP + cc);
-    }
-    // v holds channels 8cc .. 8cc+7; word cc of stored chunk j = (channel 8cc + j, channel 8cc + 4 + j)
-    const int sw = (ql >> 1) & 3;
-    unsigned* row = s_go32 + ql * 16 + cc;
-    row[(0 ^ sw) << 2] = __byte_perm(v.x, v.z, 0x5410);
-    row[(1 ^ sw) << 2] = __byte_perm(v.x, v.z, 0x7632);
-    row[(2 ^ sw) << 2] = __byte_perm(v.y, v.w, 0x5410);
-    row[(3 ^ sw) << 2] = __byte_perm(v.y, v.w, 0x7632);
-  }
-  if (tid < 16) s_go32[TQ * 16 + tid] = 0u;
 
   // per-thread samples: si = r*NT + tid; their loc / attn are prefetched one level ahead
   constexpr int SPT = NS / NT;
@@ -168,6 +166,25 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
     }
   };
   fetch_level(0);
+
+  // grad_out rows of the tile, staged once: channel-permuted and chunk-swizzled (see the file header)
+  for (int i = tid; i < TQ * LPP; i += NT) {
+    const int ql = i >> 2, cc = i & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ql < nq) {
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      v = ldg16(reinterpret_cast<const uint4*>(p.grad_out) + (((long long)b * p.Q + q) * p.H + h) * LPP + cc);
+    }
+    // v holds channels 8cc .. 8cc+7; word cc of stored chunk j = (channel 8cc + j, channel 8cc + 4 + j)
+    const int sw = go_swizzle(ql);
+    unsigned* row = s_go32 + ql * 16 + cc;
+    row[(0 ^ sw) << 2] = __byte_perm(v.x, v.z, 0x5410);
+    row[(1 ^ sw) << 2] = __byte_perm(v.x, v.z, 0x7632);
+    row[(2 ^ sw) << 2] = __byte_perm(v.y, v.w, 0x5410);
+    row[(3 ^ sw) << 2] = __byte_perm(v.y, v.w, 0x7632);
+  }
+  if (tid < 16) s_go32[TQ * 16 + tid] = 0u;
+
   if (FUSED) {
     for (int qb = 0; qb < TQ; qb += NT / 4) {
       const int ql = qb + (tid >> 2);
@@ -180,17 +197,23 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
     }
   }
 
+  auto init_misc = [&](int* m) {  // called by threads 0..15
+    int init = 0;
+    if (tid == MI_MINX || tid == MI_MINY) init = 0x7fffffff;
+    if (tid == MI_MAXX || tid == MI_MAXY) init = -1;
+    m[tid] = init;
+  };
+  if (tid < 16) init_misc(s_misc2);
+  s_cnt[tid] = 0;
+  __syncthreads();
+
+  // Barriers per level: after a, in d (2), after e, after f/g.  Phase h and the next level's phase a touch only the
+  // thread's own samples (same sample <-> thread mapping), the counters are re-armed for the next level while the
+  // current one is still running (other s_misc set after a, s_cnt after e).
   for (int l = 0; l < p.L; ++l) {
     const Level lv = p.lv[l];
     const int dxs = lv.W > 1 ? 1 : 0, dys = lv.H > 1 ? 1 : 0;
-    if (tid < 16) {
-      int init = 0;
-      if (tid == MI_MINX || tid == MI_MINY) init = 0x7fffffff;
-      if (tid == MI_MAXX || tid == MI_MAXY) init = -1;
-      s_misc[tid] = init;
-    }
-    s_cnt[tid] = 0;
-    __syncthreads();
+    int* const s_misc = s_misc2 + (l & 1) * 32;
 
     // ---- a: descriptors + bounding box (thread-local first, then one set of warp reductions)
     int t_mnx = 0x7fffffff, t_mxx = -1, t_mny = 0x7fffffff, t_mxy = -1;
@@ -225,8 +248,8 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         atomicMin(&s_misc[MI_MINY], mny); atomicMax(&s_misc[MI_MAXY], mxy);
       }
     }
-    fetch_level(l + 1);  // in flight during the sort / pull of this level
     __syncthreads();
+    if (tid < 16) init_misc(s_misc2 + ((l + 1) & 1) * 32);
 
     // ---- b: window of pixel groups (every thread computes the same rectangle); group (i, j) = pixels
     // [4*(gx_lo+i), +4) x [2*(gy_lo+j), +2)
@@ -317,11 +340,17 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         s_misc[MI_NITEMS] = (excl + v) >> 16;
       }
       if (cnt > 0) {
+        // item = (first row [0,11) | rows [11,18) | in-level mask of the group's 8 slots [18,26),
+        //         16-byte-unit offset of the group's first pixel inside the level)
         const int gyl = tid / gw, gxl = tid - gyl * gw;
+        const int px0 = (gx_lo + gxl) << 2, py0 = (gy_lo + gyl) << 1;
+        const unsigned xbits = (1u << min(lv.W - px0, 4)) - 1u;
+        const unsigned mask = xbits | (py0 + 1 < lv.H ? xbits << 4 : 0u);
+        const unsigned pixoff = (unsigned)((py0 * lv.W + px0) * (p.H * LPP));
         for (int j = 0; j * kMmaItemRows < cnt; ++j) {
           const int rb = row_start + j * kMmaItemRows;
           const int n = rb < RCAP ? min(min(kMmaItemRows, cnt - j * kMmaItemRows), RCAP - rb) : 0;
-          s_item[item_start + j] = (unsigned)gxl | ((unsigned)gyl << 6) | ((unsigned)(n ? rb : 0) << 14) | ((unsigned)n << 25);
+          s_item[item_start + j] = make_uint2((unsigned)(n ? rb : 0) | ((unsigned)n << 11) | (mask << 18), pixoff);
         }
       }
     }
@@ -340,11 +369,16 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         const int cd = code[r][k];
         if (cd >= 0) {
           const int ci = k & 1, cj = k >> 1;
+          // (a warp-aggregated rank from __match_any_sync in the histogram pass was measured: MATCH.ANY costs far more
+          // than the serialised same-address atomics it removes, 0.87 -> 1.00 ms)
           const int slot = atomicAdd(&s_cnt[cd], 1);
           if (slot < RCAP) {
             // first column / row of the footprint relative to the group: -1 = only the second one lies in it
             const int bx = ci ? -1 : (x & 3), by = cj ? -1 : (y & 1);
-            s_id[slot] = (unsigned short)(si | ((bx + 1) << 9) | ((by + 1) << 12));
+            // row code: [0,14) byte offset of the staged grad_out row incl. its swizzle, [14,23) sample, [23,26) bx + 1,
+            // [26,28) by + 1
+            const int ql = si >> LP2;
+            s_id[slot] = (unsigned)(ql * 64 + (go_swizzle(ql) << 4)) | ((unsigned)(si | ((bx + 1) << 9) | ((by + 1) << 12)) << 14);
             const float y0w = by == 0 ? a * w.z : (by == -1 ? a * w.w : 0.f);
             const float y1w = by == 1 ? a * w.z : (by == 0 ? a * w.w : 0.f);
             const unsigned p0 = Vec16<VT>::pack2(y0w * w.x, y0w * w.y), p1 = Vec16<VT>::pack2(y1w * w.x, y1w * w.y);
@@ -368,6 +402,7 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
       }
     }
     __syncthreads();
+    s_cnt[tid] = 0;  // for the next level's histogram
 
     // ---- f: pull.  Warp-level: item -> 8 value rows -> row blocks of 16.  The value rows of the next item are
     // requested before the current one is processed.
@@ -375,42 +410,52 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
       const int g8 = lane >> 2, t4 = lane & 3;
       const int n_items = s_misc[MI_NITEMS];
       const int pix16 = p.H * LPP;  // 16-byte units per pixel
-      const uint4* const v_lane = vrow + (lv.start * p.H + h) * LPP + t4;
-      float* const acc_lane = acc_f + (long long)((lv.start * p.H + h) * LPP) * 8 + 4 * g8;
-      const int vsx = g8 & 3, vsy = g8 >> 2;           // slot whose value row this lane loads
-      const int kx = 2 * (t4 & 1) + 1, ky = (t4 >> 1) + 1;  // this lane's dot columns: slots 2*t4, 2*t4 + 1
-      auto load_v = [&](unsigned item) -> uint4 {
-        const int x = ((gx_lo + (int)(item & 63)) << 2) + vsx, y = ((gy_lo + (int)((item >> 6) & 255)) << 1) + vsy;
-        if ((item >> 25) != 0u && x < lv.W && y < lv.H) return ldg16(v_lane + (y * lv.W + x) * pix16);
+      // lane (g8, t4): value row of slot g8 (x = g8 % 4, y = g8 / 4), channels 8*t4 .. +7; accumulator channels
+      // 4*g8 .. +3 of slots 2*t4 and 2*t4 + 1 (x = 2*(t4 % 2) (+1), y = t4 / 2)
+      const uint4* const v_lane = vrow + (lv.start * p.H + h) * LPP + ((g8 >> 2) * lv.W + (g8 & 3)) * pix16 + t4;
+      float* const acc_lane = acc_f + (long long)((lv.start * p.H + h) * LPP + ((t4 >> 1) * lv.W + 2 * (t4 & 1)) * pix16) * 8 + 4 * g8;
+      const int kx = 2 * (t4 & 1) + 1, ky = (t4 >> 1) + 1;
+      const unsigned vbit = 1u << (18 + g8), fbit = 1u << (18 + 2 * t4);
+      const unsigned lsel = ((unsigned)lane >> 4) << 4;  // chunk select of the ldmatrix row addresses
+      auto load_v = [&](uint2 item) -> uint4 {
+        if (item.x & vbit) return ldg16(v_lane + (int)item.y);
         return make_uint4(0u, 0u, 0u, 0u);
       };
       int it = warp;
-      unsigned item = it < n_items ? s_item[it] : 0u;
+      uint2 item = it < n_items ? s_item[it] : make_uint2(0u, 0u);
       uint4 vv = load_v(item);
       while (it < n_items) {
         const int it_n = it + NW;
-        const unsigned item_n = it_n < n_items ? s_item[it_n] : 0u;
+        const uint2 item_n = it_n < n_items ? s_item[it_n] : make_uint2(0u, 0u);
         const uint4 vv_n = load_v(item_n);
-        const int n = (int)(item >> 25);
+        const int n = (int)((item.x >> 11) & 127u);
         if (n != 0) {
-          const int rbeg = (int)((item >> 14) & 0x7ff), rend = rbeg + n;
+          const int rbeg = (int)(item.x & 0x7ffu), rend = rbeg + n;
           const unsigned bv00 = __byte_perm(vv.x, vv.z, 0x5410);  // channels 8t, 8t+4   <-> k = 2t, 2t+1 of chunk 0
           const unsigned bv01 = __byte_perm(vv.x, vv.z, 0x7632);  // channels 8t+1, 8t+5 <-> chunk 1
           const unsigned bv10 = __byte_perm(vv.y, vv.w, 0x5410);  // channels 8t+2, 8t+6 <-> chunk 2
           const unsigned bv11 = __byte_perm(vv.y, vv.w, 0x7632);  // channels 8t+3, 8t+7 <-> chunk 3
           float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int r0 = rbeg; r0 < rend; r0 += 16) {
+          // row codes are fetched one row block ahead
+          const unsigned kNoRow = 0x0fffc000u | (unsigned)(TQ * 64);  // all-zero grad_out row, matches no (sample, corner)
+          int r0 = rbeg;
+          unsigned code_l = r0 + (lane & 15) < rend ? s_id[r0 + (lane & 15)] : kNoRow;
+          while (true) {
+            const int rn = r0 + 16;
+            const unsigned code_ln = rn + (lane & 15) < rend ? s_id[rn + (lane & 15)] : kNoRow;
             const int idx = r0 + (lane & 15);
-            const bool rv = idx < rend;
-            const unsigned code_l = rv ? (unsigned)s_id[idx] : 0xffffu;  // 0xffff: no (sample, corner) matches below
-            const int ql = rv ? (int)((code_l & 511u) >> LP2) : TQ;
-            const unsigned ga = go_sa + ql * 64 + ((((unsigned)lane >> 4) ^ ((ql >> 1) & 3)) << 4);
+            const unsigned ga = go_sa + ((code_l & 0x3fffu) ^ lsel);
             unsigned a[4], a2[4], tA[4], tB[4], bw[2];
             ldsm_x4(a, ga);
             ldsm_x4(a2, ga ^ 32u);
+#if MSDA_MMA_MOVM
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tA[j] = movm_trans(a[j]); tB[j] = movm_trans(a2[j]); }
+#else
             ldsm_x4_trans(tA, ga);
             ldsm_x4_trans(tB, ga ^ 32u);
-            ldsm_x2_trans(bw, rv ? wrow_sa + idx * 16 : go_sa + TQ * 64);
+#endif
+            ldsm_x2_trans(bw, idx < rend ? wrow_sa + idx * 16 : go_sa + TQ * 64);
             float d[4] = {0.f, 0.f, 0.f, 0.f};
             mma_bf16(d, a[0], a[1], a[2], a[3], bv00, bv01);
             mma_bf16(d, a2[0], a2[1], a2[2], a2[3], bv10, bv11);
@@ -420,25 +465,28 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const unsigned code = __shfl_sync(0xffffffffu, code_l, g8 + 8 * e);
-              const int cxa = kx - (int)((code >> 9) & 7u), cy = ky - (int)((code >> 12) & 3u);
-              float* dst = s_dot + (code & 511u) * 4 + cy * 2 + cxa;
+              const int cxa = kx - (int)((code >> 23) & 7u), cy = ky - (int)((code >> 26) & 3u);
+              float* dst = s_dot + ((code >> 14) & 511u) * 4 + cy * 2 + cxa;
               if ((unsigned)cy < 2u && (unsigned)cxa < 2u) dst[0] = d[2 * e];
               if ((unsigned)cy < 2u && (unsigned)(cxa + 1) < 2u) dst[1] = d[2 * e + 1];
             }
+            if (rn >= rend) break;
+            r0 = rn; code_l = code_ln;
           }
           // flush: lane (g8, t4) holds channels 4*g8 .. +3 of slots 2*t4 (acc*[0], acc*[2]) and 2*t4 + 1 (acc*[1], acc*[3])
-          const int sxa = ((gx_lo + (int)(item & 63)) << 2) + kx - 1, sya = ((gy_lo + (int)((item >> 6) & 255)) << 1) + ky - 1;
-          float* const dst = acc_lane + (long long)((sya * lv.W + sxa) * pix16) * 8;
+          float* const dst = acc_lane + (long long)(int)item.y * 8;
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
             const float v0 = acc0[s], v1 = acc0[2 + s], v2 = acc1[s], v3 = acc1[2 + s];
-            if (sxa + s < lv.W && sya < lv.H && (v0 != 0.f || v1 != 0.f || v2 != 0.f || v3 != 0.f))
-              red_add_f32x4(dst + s * pix16 * 8, v0, v1, v2, v3);
+            const unsigned nz = (__float_as_uint(v0) | __float_as_uint(v1) | __float_as_uint(v2) | __float_as_uint(v3)) << 1;
+            if ((item.x & (fbit << s)) && nz != 0u) red_add_f32x4(dst + s * pix16 * 8, v0, v1, v2, v3);
           }
         }
         it = it_n; item = item_n; vv = vv_n;
       }
     }
+
+    fetch_level(l + 1);  // in flight during the fallback pass and the per-sample gradients of this level
 
     // ---- g: fallback contributions (outside the window / row list full): direct reduction, four lanes per corner
     {
@@ -455,7 +503,7 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         Vec16<VT>::unpack(ldg16(vrow + off + c), vf);
         {
           // lane c needs channels 8c .. 8c+7: word c of stored chunk j = (channel 8c + j, channel 8c + 4 + j)
-          const int ql = si >> LP2, sw = (ql >> 1) & 3;
+          const int ql = si >> LP2, sw = go_swizzle(ql);
           const unsigned* row = s_go32 + ql * 16 + c;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -511,13 +559,13 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         float t = valid ? a * g_attn : 0.f;  // the P samples of one (query, level) sit in P adjacent lanes
 #pragma unroll
         for (int o = 1; o < P; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (valid && pt == 0) s_dsum[ql] += t;  // one writer per query and level; levels are separated by barriers
+        if (valid && pt == 0) s_dsum[ql] += t;  // one writer (always the same thread) per query
       }
     }
-    __syncthreads();
   }
 
   if (FUSED) {
+    __syncthreads();
     // softmax backward over the L*P logits of each (query, head): g_j = a_j * (ga_j - sum_k a_k ga_k)
     for (int i = tid; i < nq * p.LP; i += NT) {
       const int ql = i / p.LP, sidx = i - ql * p.LP;
