@@ -241,6 +241,8 @@ class Problem:
         self.flags = _cabi.FLAG_BF16_ATOMICS if (functional._BF16_ATOMICS and dtype == "bf16") else 0
         if functional._BWD_V1:
             self.flags |= _cabi.FLAG_BWD_V1
+        if functional._BWD_V2:
+            self.flags |= _cabi.FLAG_BWD_V2
         self.desc, self._keep = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi, self.flags)
         self.pdesc, self._keep2 = _cabi.make_desc(batch, self.S, self.S, H, D, L, P, code, code, shapes, lsi,
                                                   self.flags | _cabi.FLAG_PROFILE)
@@ -454,8 +456,9 @@ def run_b200(args, rank, world, local_rank):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {
         "bound": "hbm",
-        "kernel": ("msda_bwd_sorted_kernel" if (args.dtype == "bf16" and not (prob.flags & _cabi.FLAG_BWD_V1))
-                   else "msda_bwd_kernel") if dominant == "bwd_main" else "msda_fwd_pair_kernel",
+        "kernel": (("msda_bwd_kernel" if (args.dtype != "bf16" or (prob.flags & _cabi.FLAG_BWD_V1)) else
+                    "msda_bwd_sorted_kernel" if (prob.flags & (_cabi.FLAG_BWD_V2 | _cabi.FLAG_BF16_ATOMICS)) else
+                    "msda_bwd_mma_kernel") if dominant == "bwd_main" else "msda_fwd_pair_kernel"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms, "traffic": recorded_traffic(dominant),
     }
