@@ -293,7 +293,11 @@ __global__ void __launch_bounds__(NT) msda_fwd_kernel(const __grid_constant__ KP
 // groups of a block alternate between an even and an odd head, so the two 64-byte runs of every quarter-warp fall into
 // different halves and the request is conflict-free (127 B/clk/SM measured). It also makes every fetched 128-byte line
 // fully useful. Virtual query v = ql * HPB + hl  <->  query q0 + ql, head h0 + hl.
-template <typename VT, typename AT, int D, int NT, int QPG, int HPB, bool FUSED>
+// LC: compile-time level count with P == 4 (0 = generic L / P from the descriptor).  With LC != 0 one thread builds the
+// four descriptors of one (query, head, level): its locations are one 32-byte run, its attention weights one 8- or
+// 16-byte run, and the index arithmetic (runtime divisions by L*P and P in the generic loop) is paid once per four
+// samples -- the descriptor phase was 42 % of the forward (ncu r02_fwd_pair).
+template <typename VT, typename AT, int D, int NT, int QPG, int HPB, bool FUSED, int LC>
 __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant__ KParams p) {
   constexpr int VEC = Vec16<VT>::N;
   constexpr int LPP = D / VEC;
@@ -313,7 +317,9 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   const int q0 = tile * TQ;
   const int nq = min(TQ, p.Q - q0);
   const int nv = nq * HPB;
-  const int LP = p.LP;
+  const int LP = LC ? LC * 4 : p.LP;
+  // (Measured and dropped: one block walking 2 / 4 / 8 consecutive strips of a patch so that later strips find the
+  // value rows in L1 -- 0.291 / 0.301 / 0.325 ms against 0.291 for one strip per block, profiles/r02_notes.md.)
 
   if (FUSED) {
     tile_softmax<AT, NT, HPB>(p, b, h0, q0, nq, s_att, true);
@@ -321,21 +327,79 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   }
 
   // ---- phase 1: descriptors (the LP samples of the HPB heads of one query are adjacent in memory)
-  for (int i = threadIdx.x; i < nv * LP; i += NT) {
-    const int v = i / LP, s = i - v * LP;
-    const int ql = v / HPB, h = h0 + v % HPB;
-    const int l = s / p.P;
-    const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
-    const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
-    const Level lv = p.lv[l];
-    const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, q, lv)
-                            : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
-    const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
-    const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
-    const bool ok = ax.ok && ay.ok;
-    const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
-    sw[s * ROW + v] = make_float4(wt * ax.s0, wt * ax.s1, wb * ax.s0, wb * ax.s1);
-    soff[s * ROW + v] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+  if (LC) {
+    constexpr int PC = 4;
+    for (int i = threadIdx.x; i < nv * LC; i += NT) {
+      const int v = i / (LC ? LC : 1), l = i - v * LC;
+      const int ql = v / HPB, h = h0 + v % HPB;
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const long long si = (((long long)b * p.Q + q) * p.H + h) * (LC * PC) + l * PC;
+      const Level lv = p.lv[l];
+      float2 xy[PC];
+      float a[PC];
+      if (FUSED) {
+        const float2 r = p.ref ? __ldg(reinterpret_cast<const float2*>(p.ref) + ((long long)b * p.Q + q) * LC + l)
+                               : implicit_reference_point(p, q);
+        float2 off[PC];
+        if (std::is_same<AT, float>::value) {
+          const float4 o0 = __ldg(reinterpret_cast<const float4*>(p.offsets) + si / 2);
+          const float4 o1 = __ldg(reinterpret_cast<const float4*>(p.offsets) + si / 2 + 1);
+          off[0] = make_float2(o0.x, o0.y); off[1] = make_float2(o0.z, o0.w);
+          off[2] = make_float2(o1.x, o1.y); off[3] = make_float2(o1.z, o1.w);
+        } else {
+          const uint4 o = ldg16(reinterpret_cast<const uint4*>(p.offsets) + si / 4);
+          float f[8];
+          Vec16<__nv_bfloat16>::unpack(o, f);
+#pragma unroll
+          for (int pt = 0; pt < PC; ++pt) off[pt] = make_float2(f[2 * pt], f[2 * pt + 1]);
+        }
+#pragma unroll
+        for (int pt = 0; pt < PC; ++pt) {
+          xy[pt] = make_float2(__fadd_rn(r.x, __fdiv_rn(off[pt].x, (float)lv.W)), __fadd_rn(r.y, __fdiv_rn(off[pt].y, (float)lv.H)));
+          a[pt] = s_att[v * (LC * PC) + l * PC + pt];
+        }
+      } else {
+        const float4 l0 = __ldg(reinterpret_cast<const float4*>(p.loc) + si / 2);
+        const float4 l1 = __ldg(reinterpret_cast<const float4*>(p.loc) + si / 2 + 1);
+        xy[0] = make_float2(l0.x, l0.y); xy[1] = make_float2(l0.z, l0.w);
+        xy[2] = make_float2(l1.x, l1.y); xy[3] = make_float2(l1.z, l1.w);
+        if (std::is_same<AT, float>::value) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.attn) + si / 4);
+          a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+        } else {
+          const uint2 t = __ldg(reinterpret_cast<const uint2*>(p.attn) + si / 4);
+          a[0] = __uint_as_float(t.x << 16); a[1] = __uint_as_float(t.x & 0xffff0000u);
+          a[2] = __uint_as_float(t.y << 16); a[3] = __uint_as_float(t.y & 0xffff0000u);
+        }
+      }
+      const int pix0 = lv.start * p.H + h;
+#pragma unroll
+      for (int pt = 0; pt < PC; ++pt) {
+        const Axis ax = axis_setup(xy[pt].x, lv.W), ay = axis_setup(xy[pt].y, lv.H);
+        const bool ok = ax.ok && ay.ok;
+        const float wt = ok ? a[pt] * ay.s0 : 0.f, wb = ok ? a[pt] * ay.s1 : 0.f;
+        const int s = l * PC + pt;
+        sw[s * ROW + v] = make_float4(wt * ax.s0, wt * ax.s1, wb * ax.s0, wb * ax.s1);
+        soff[s * ROW + v] = (pix0 + (ay.base * lv.W + ax.base) * p.H) * LPP;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < nv * LP; i += NT) {
+      const int v = i / LP, s = i - v * LP;
+      const int ql = v / HPB, h = h0 + v % HPB;
+      const int l = s / p.P;
+      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+      const long long si = (((long long)b * p.Q + q) * p.H + h) * LP + s;
+      const Level lv = p.lv[l];
+      const float2 xy = FUSED ? fused_loc<AT>(p, si, ((long long)b * p.Q + q) * p.L + l, q, lv)
+                              : __ldg(reinterpret_cast<const float2*>(p.loc) + si);
+      const float a = FUSED ? s_att[i] : to_float<AT>(reinterpret_cast<const AT*>(p.attn)[si]);
+      const Axis ax = axis_setup(xy.x, lv.W), ay = axis_setup(xy.y, lv.H);
+      const bool ok = ax.ok && ay.ok;
+      const float wt = ok ? a * ay.s0 : 0.f, wb = ok ? a * ay.s1 : 0.f;
+      sw[s * ROW + v] = make_float4(wt * ax.s0, wt * ax.s1, wb * ax.s0, wb * ax.s1);
+      soff[s * ROW + v] = ((lv.start + ay.base * lv.W + ax.base) * p.H + h) * LPP;
+    }
   }
   __syncthreads();
 
@@ -349,11 +413,12 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    for (int l = 0; l < p.L; ++l) {
+    const int nl = LC ? LC : p.L, np = LC ? 4 : p.P;
+    for (int l = 0; l < nl; ++l) {
       const int dx = p.lv[l].dx16, dy = p.lv[l].dy16;
 #pragma unroll 4
-      for (int pt = 0; pt < p.P; ++pt) {
-        const int s = l * p.P + pt;
+      for (int pt = 0; pt < np; ++pt) {
+        const int s = l * np + pt;
         gather_sample<VT, VEC, false>(vb + soff[s * ROW + v], dx, dy, sw[s * ROW + v], acc);
       }
     }
@@ -677,6 +742,11 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   return check_launch("msda_b200_forward");
 }
 
+int env_cfg(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 // Forward with two heads per block (see msda_fwd_pair_kernel). NT / QPG from the environment for tuning runs only.
 template <typename VT, typename AT, int D, int NT, int QPG, bool FUSED>
 int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
@@ -684,7 +754,8 @@ int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int LPP = D / Vec16<VT>::N, NG = NT / LPP, TV = NG * QPG, TQ = TV / HPB, ROW = TV + 1;
   fill_geometry(d, p, TQ);
   const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int)) + (FUSED ? (size_t)TV * p.LP * sizeof(float) : 0);
-  auto kern = msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED>;
+  auto kern = (d->L == 3 && d->P == 4) ? msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED, 3>
+                                       : msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED, 0>;
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
@@ -696,11 +767,6 @@ int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
     ++g_launches;
   }
   return check_launch("msda_b200_forward (head pairs)");
-}
-
-int env_cfg(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
 }
 
 template <typename VT, typename AT, int D, bool FUSED>
