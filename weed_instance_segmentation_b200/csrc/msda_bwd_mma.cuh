@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
       uint2 item = it < n_items ? s_item[it] : make_uint2(0u, 0u);
       uint4 vv = load_v(item);
       while (it < n_items) {
-        const int it_n = it + NW;
+        const int it_n = it + NW;  // (items handed out on demand through an atomic counter were measured slower: 0.885 vs 0.867 ms)
         const uint2 item_n = it_n < n_items ? s_item[it_n] : make_uint2(0u, 0u);
         const uint4 vv_n = load_v(item_n);
         const int n = (int)((item.x >> 11) & 127u);
@@ -487,7 +487,10 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
       }
     }
 
-    fetch_level(l + 1);  // in flight during the fallback pass and the per-sample gradients of this level
+    // in flight during the fallback pass and the per-sample gradients of this level (issued before the pull it would
+    // hide its latency better, but its six registers push the pull over the 64-register budget of 4 blocks / SM:
+    // spills, 0.887 vs 0.867 ms)
+    fetch_level(l + 1);
 
     // ---- g: fallback contributions (outside the window / row list full): direct reduction, four lanes per corner
     {
