@@ -1,7 +1,7 @@
 """Summarise an ncu report of one kernel: headline counters, then instructions / stall samples / shared-memory
 wavefronts per barrier-delimited code segment (ncu --import-source on, read here without a GPU).
 
-    python tools/ncu_segments.py gpurun_out/x.ncu-rep [--list FIRST LAST]
+    python tools/ncu_segments.py gpurun_out/x.ncu-rep [--kernel REGEX] [--list FIRST LAST]
 """
 import csv
 import io
@@ -9,7 +9,9 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# optional kernel filter for reports that hold several kernels: --kernel REGEX (first matching launch)
+sel = ["-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1], "-c", "1"] if "--kernel" in sys.argv else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", *sel], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
 want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -23,11 +25,17 @@ want = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
 for h, v in zip(hdr, vals):
     if h in want:
         print(f"{h} = {v}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", *sel], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 print(rows[0][1][:140])
 ix = {h: i for i, h in enumerate(rows[1])}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(rows[1]) and r[0].startswith("0x")]  # SASS view only
+seen = set()
+for k, r in enumerate(data):  # some ncu versions print the listing twice
+    if r[0] in seen:
+        data = data[:k]
+        break
+    seen.add(r[0])
 num = lambda r, k: int(r[ix[k]] or 0)  # noqa: E731
 tot = sum(num(r, "Instructions Executed") for r in data)
 tots = sum(num(r, "# Samples") for r in data)
