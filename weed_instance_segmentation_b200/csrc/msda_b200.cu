@@ -719,6 +719,11 @@ int check_launch(const char* what) {
 constexpr int kFwdNT = 128, kFwdQPG = 1;  // measured on config 2: 0.332 ms (256/1: 0.347, 256/2: 0.332, 512/1: 0.410)
 constexpr int kBwdNT = 128, kBwdQPG = 1;
 
+int env_cfg(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 template <typename VT, typename AT, int D, bool FUSED>
 int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int LPP = D / Vec16<VT>::N;
@@ -732,6 +737,8 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
+  if (const int carve = env_cfg("MSDA_B200_FWD1_CARVEOUT", -1); carve >= 0)  // tuning runs (see launch_fwd_pair_cfg)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   const long long blocks = (long long)p.B * p.num_tiles * p.H;
   if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "forward: grid too large");
   {
@@ -740,11 +747,6 @@ int launch_fwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
     ++g_launches;
   }
   return check_launch("msda_b200_forward");
-}
-
-int env_cfg(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
 }
 
 // Forward with two heads per block (see msda_fwd_pair_kernel). NT / QPG from the environment for tuning runs only.
@@ -759,6 +761,13 @@ int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "forward: cannot reserve %zu bytes of shared memory", smem);
+  // Shared-memory carve-out: what is left of the SM's 256 KB is the L1 the gather lives in. The driver's default makes
+  // room for the register limit's 9 blocks; 50 % (132 KB) holds 7 blocks of the plain kernel and leaves the gather
+  // 124 KB of L1. Measured (profiles/r02_notes.md; config 2 init / trained, config 3 init / trained, ms): default
+  // 0.286 / 0.306 / 0.661 / 0.717, 50 %: 0.282 / 0.301 / 0.655 / 0.696, 40 %: 0.313 / 0.337 / 0.697 / 0.747. The fused
+  // prologue's blocks are 3 KB larger (softmax tile), 50 % holds only 6 of them: 0.407 vs 0.321 ms -> driver default.
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       env_cfg("MSDA_B200_FWD_CARVEOUT", FUSED ? -1 : 50));
   const long long blocks = (long long)p.B * p.num_tiles * (p.H / HPB);
   if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "forward: grid too large");
   {
@@ -789,6 +798,8 @@ int launch_bwd(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(MSDA_B200_ERR_CUDA, "backward: cannot reserve %zu bytes of shared memory", smem);
+  if (const int carve = env_cfg("MSDA_B200_BWD1_CARVEOUT", -1); carve >= 0)  // tuning runs (see launch_fwd_pair_cfg)
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
   const long long blocks = (long long)p.B * p.num_tiles * p.H;
   if (blocks > 0x7fffffffll) return fail(MSDA_B200_ERR_UNSUPPORTED, "backward: grid too large");
   {

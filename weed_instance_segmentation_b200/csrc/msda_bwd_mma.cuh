@@ -92,7 +92,7 @@ __host__ __device__ inline MmaSmem mma_smem_layout() {
   s.fb = o;   o += sizeof(unsigned short) * NS * 4;
   o = (o + 15) & ~size_t(15);
   s.misc = o; o += sizeof(int) * 64;
-  s.stat = o; o += FUSED ? sizeof(float) * 3 * TQ : 0;
+  s.stat = o;  // (fused prologue: the softmax statistics live in registers, see f_lse / f_dsum)
   s.total = o;
   return s;
 }
@@ -124,9 +124,6 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
   unsigned* s_id = reinterpret_cast<unsigned*>(smem_raw + lay.id);
   unsigned short* s_fb = reinterpret_cast<unsigned short*>(smem_raw + lay.fb);
   int* const s_misc2 = reinterpret_cast<int*>(smem_raw + lay.misc);  // two sets of 32, alternating by level
-  float* s_max = reinterpret_cast<float*>(smem_raw + lay.stat);
-  float* s_inv = s_max + TQ;
-  float* s_dsum = s_inv + TQ;
 
   int b, tile, h;
   decode_block(p, b, tile, h);
@@ -185,15 +182,24 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
   }
   if (tid < 16) s_go32[TQ * 16 + tid] = 0u;
 
+  // Fused prologue: the P = 4 samples (r, tid) of one (query, level) sit in four adjacent lanes, and sample r of every
+  // level belongs to query r * NT / P + tid / P -- so the softmax statistics of a thread's own queries never leave its
+  // registers: f_lse = max + log(sum exp(x - max)) (a_j = exp(x_j - f_lse)), f_dsum = sum_k a_k * d(loss)/d(a_k).
+  // (In shared memory they cost 1.5 KB per block, which took the fused kernel from 4 to 3 blocks per SM.)
+  static_assert(!FUSED || P == 4, "fused prologue: four lanes per (query, head) row");
+  float f_lse[SPT], f_dsum[SPT];
+#pragma unroll
+  for (int r = 0; r < SPT; ++r) { f_lse[r] = 0.f; f_dsum[r] = 0.f; }
   if (FUSED) {
-    for (int qb = 0; qb < TQ; qb += NT / 4) {
-      const int ql = qb + (tid >> 2);
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int ql = (r * NT + tid) >> LP2;
       const bool valid = ql < nq;
       const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
       float mx, inv;
       softmax_stats_x4<AT>(reinterpret_cast<const AT*>(p.logits) + (((long long)b * p.Q + q) * p.H + h) * p.LP, p.LP,
                            tid & 3, valid, mx, inv);
-      if ((tid & 3) == 0) { s_max[ql] = valid ? mx : 0.f; s_inv[ql] = inv; s_dsum[ql] = 0.f; }
+      f_lse[r] = valid ? mx - logf(inv) : 0.f;
     }
   }
 
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
       float a = 0.f;
       int xb = 0, yb = 0;
       if (ql < nq) {
-        a = FUSED ? expf(pre_a[r] - s_max[ql]) * s_inv[ql] : pre_a[r];
+        a = FUSED ? expf(pre_a[r] - f_lse[r]) : pre_a[r];
         const Axis ax = axis_setup(pre_loc[r].x, lv.W), ay = axis_setup(pre_loc[r].y, lv.H);
         xb = ax.base; yb = ay.base;
         if (ax.ok && ay.ok) {
@@ -532,7 +538,9 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
     __syncthreads();
 
     // ---- h: per-sample gradients; a corner that is not read (derivative code 1) has no dot
-    for (int si = tid; si < NS; si += NT) {
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int si = r * NT + tid;
       const int ql = si >> LP2, pt = si & (P - 1);
       const bool valid = ql < nq;
       const int q = valid ? (p.q_order ? p.q_order[q0 + ql] : q0 + ql) : 0;
@@ -563,21 +571,28 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         float t = valid ? a * g_attn : 0.f;  // the P samples of one (query, level) sit in P adjacent lanes
 #pragma unroll
         for (int o = 1; o < P; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (valid && pt == 0) s_dsum[ql] += t;  // one writer (always the same thread) per query
+        f_dsum[r] += t;  // every one of the four lanes keeps the row's sum
       }
     }
   }
 
   if (FUSED) {
-    __syncthreads();
-    // softmax backward over the L*P logits of each (query, head): g_j = a_j * (ga_j - sum_k a_k ga_k)
-    for (int i = tid; i < nq * p.LP; i += NT) {
-      const int ql = i / p.LP, sidx = i - ql * p.LP;
-      const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
-      const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + sidx;
-      const float a = expf(to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]) - s_max[ql]) * s_inv[ql];
-      const float ga = to_float<AT>(reinterpret_cast<const AT*>(p.grad_logits)[gi]);
-      reinterpret_cast<AT*>(p.grad_logits)[gi] = from_float<AT>(a * (ga - s_dsum[ql]));
+    // softmax backward over the L*P logits of each (query, head): g_j = a_j * (ga_j - sum_k a_k ga_k).  Lane pt of the
+    // row's four lanes finishes the logits (l, pt) of every level l -- exactly the ones it parked itself in phase h, so
+    // no barrier is needed.
+#pragma unroll
+    for (int r = 0; r < SPT; ++r) {
+      const int ql = (r * NT + tid) >> LP2, pt = tid & (P - 1);
+      if (ql < nq) {
+        const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
+        const long long row = (((long long)b * p.Q + q) * p.H + h) * p.LP;
+        for (int l = 0; l < p.L; ++l) {
+          const long long gi = row + l * P + pt;
+          const float a = expf(to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]) - f_lse[r]);
+          const float ga = to_float<AT>(reinterpret_cast<const AT*>(p.grad_logits)[gi]);
+          reinterpret_cast<AT*>(p.grad_logits)[gi] = from_float<AT>(a * (ga - f_dsum[r]));
+        }
+      }
     }
   }
 }
