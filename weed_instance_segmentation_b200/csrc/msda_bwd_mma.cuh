@@ -378,6 +378,8 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
           // Measured and dropped: warp-aggregated ranks from __match_any_sync in the histogram pass (MATCH.ANY costs far
           // more than the serialised same-address atomics it removes, 0.87 -> 1.00 ms); dealing the query slots out so
           // that one instruction's eight queries lie >= 4 pixels apart (fewer same-address lanes, 0.87 -> 0.90 ms).
+          // (also measured and dropped: keeping the rank the histogram pass's atomic returned, packed into `code`, and
+          // replacing this second round of atomics by a broadcast LDS of the group's start -- 0.877 vs 0.867 ms)
           const int slot = atomicAdd(&s_cnt[cd], 1);
           if (slot < RCAP) {
             // first column / row of the footprint relative to the group: -1 = only the second one lies in it
