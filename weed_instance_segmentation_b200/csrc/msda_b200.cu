@@ -634,7 +634,14 @@ bool prof_prepare() {
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   if (g_prof.device == dev) return true;
   if (g_prof.device >= 0) {
-    // events belong to another device's context; leak them rather than switch devices here
+    // the old events belong to another device: release them there, then come back
+    if (cudaSetDevice(g_prof.device) == cudaSuccess)
+      for (int i = 0; i < MSDA_B200_PROF_COUNT; ++i) {
+        cudaEventDestroy(g_prof.ev[i][0]);
+        cudaEventDestroy(g_prof.ev[i][1]);
+      }
+    g_prof.device = -1;
+    if (cudaSetDevice(dev) != cudaSuccess) return false;
   }
   for (int i = 0; i < MSDA_B200_PROF_COUNT; ++i) {
     if (cudaEventCreate(&g_prof.ev[i][0]) != cudaSuccess) return false;
