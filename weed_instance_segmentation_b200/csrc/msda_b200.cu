@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   float4* sw = reinterpret_cast<float4*>(smem_raw);                                         // [LP][ROW] slot weights * attn
   int* soff = reinterpret_cast<int*>(smem_raw + (size_t)p.LP * ROW * sizeof(float4));       // [LP][ROW]
   float* s_att = reinterpret_cast<float*>(soff + (size_t)p.LP * ROW);                       // FUSED: [TV][LP] softmax
+  float* s_ref = s_att + (size_t)TV * p.LP;                                                 // FUSED: [TQ][2] implicit ref points
+  static_assert(TQ <= NT, "one thread per query computes its reference point");
 
   int bid = blockIdx.x;
   const int hgroups = p.H / HPB;
@@ -322,6 +324,12 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   // value rows in L1 -- 0.291 / 0.301 / 0.325 ms against 0.291 for one strip per block, profiles/r02_notes.md.)
 
   if (FUSED) {
+    // implicit reference points: once per query of the tile (they depend on neither head nor level)
+    if (!p.ref && threadIdx.x < nq) {
+      const float2 r = implicit_reference_point(p, p.q_order ? p.q_order[q0 + threadIdx.x] : q0 + threadIdx.x);
+      s_ref[2 * threadIdx.x] = r.x;
+      s_ref[2 * threadIdx.x + 1] = r.y;
+    }
     tile_softmax<AT, NT, HPB>(p, b, h0, q0, nq, s_att, true);
     __syncthreads();
   }
@@ -338,8 +346,7 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
       float2 xy[PC];
       float a[PC];
       if (FUSED) {
-        const float2 r = p.ref ? __ldg(reinterpret_cast<const float2*>(p.ref) + ((long long)b * p.Q + q) * LC + l)
-                               : implicit_reference_point(p, q);
+        const float2 r = p.ref ? __ldg(reinterpret_cast<const float2*>(p.ref) + ((long long)b * p.Q + q) * LC + l) : make_float2(s_ref[2 * ql], s_ref[2 * ql + 1]);
         float2 off[PC];
         if (std::is_same<AT, float>::value) {
           const float4 o0 = __ldg(reinterpret_cast<const float4*>(p.offsets) + si / 2);
@@ -762,7 +769,7 @@ int launch_fwd_pair_cfg(const msda_b200_desc* d, KParams p, cudaStream_t st) {
   constexpr int HPB = 2;
   constexpr int LPP = D / Vec16<VT>::N, NG = NT / LPP, TV = NG * QPG, TQ = TV / HPB, ROW = TV + 1;
   fill_geometry(d, p, TQ);
-  const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int)) + (FUSED ? (size_t)TV * p.LP * sizeof(float) : 0);
+  const size_t smem = (size_t)p.LP * ROW * (sizeof(float4) + sizeof(int)) + (FUSED ? (size_t)TV * p.LP * sizeof(float) + (size_t)TQ * sizeof(float2) : 0);
   auto kern = (d->L == 3 && d->P == 4) ? msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED, 3>
                                        : msda_fwd_pair_kernel<VT, AT, D, NT, QPG, HPB, FUSED, 0>;
   if (smem > 48 * 1024 &&

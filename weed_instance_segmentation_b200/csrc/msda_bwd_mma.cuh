@@ -142,6 +142,13 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
   constexpr int SPT = NS / NT;
   float2 pre_loc[SPT];
   float pre_a[SPT];
+  float2 f_ref[SPT];  // fused prologue with implicit reference points: the thread's queries' own pixel centres
+#pragma unroll
+  for (int r = 0; r < SPT; ++r) {
+    f_ref[r] = make_float2(0.f, 0.f);
+    const int ql = (r * NT + tid) >> LP2;
+    if (FUSED && !p.ref && ql < nq) f_ref[r] = implicit_reference_point(p, p.q_order ? p.q_order[q0 + ql] : q0 + ql);
+  }
   auto fetch_level = [&](int l) {
 #pragma unroll
     for (int r = 0; r < SPT; ++r) {
@@ -153,7 +160,13 @@ __global__ void __launch_bounds__(NT, 4) msda_bwd_mma_kernel(const __grid_consta
         const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
         const long long gi = (((long long)b * p.Q + q) * p.H + h) * p.LP + l * P + pt;
         if (FUSED) {
-          pre_loc[r] = fused_loc<AT>(p, gi, ((long long)b * p.Q + q) * p.L + l, q, p.lv[l]);
+          // loc = ref + off / (W_l, H_l) (M2F:963-971); the implicit reference point of a query (ref == NULL) does not
+          // depend on the level and was computed once in f_ref
+          const float2 off = load_pair<AT>(p.offsets, gi);
+          const float2 rp = p.ref ? __ldg(reinterpret_cast<const float2*>(p.ref) + ((long long)b * p.Q + q) * p.L + l)
+                                  : f_ref[r];
+          pre_loc[r] = make_float2(__fadd_rn(rp.x, __fdiv_rn(off.x, (float)p.lv[l].W)),
+                                   __fadd_rn(rp.y, __fdiv_rn(off.y, (float)p.lv[l].H)));
           pre_a[r] = to_float<AT>(reinterpret_cast<const AT*>(p.logits)[gi]);  // raw logit; softmax applied at use
         } else {
           pre_loc[r] = __ldg(reinterpret_cast<const float2*>(p.loc) + gi);
