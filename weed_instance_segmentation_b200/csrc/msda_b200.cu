@@ -337,8 +337,12 @@ __global__ void __launch_bounds__(NT) msda_fwd_pair_kernel(const __grid_constant
   // ---- phase 1: descriptors (the LP samples of the HPB heads of one query are adjacent in memory)
   if (LC) {
     constexpr int PC = 4;
-    for (int i = threadIdx.x; i < nv * LC; i += NT) {
-      const int v = i / (LC ? LC : 1), l = i - v * LC;
+    // thread <-> (level, virtual query) with the virtual query on the fast axis: the float4 descriptor stores of a
+    // quarter-warp then fall into eight different 16-byte bank groups (level-fastest, rows 4 * ROW * 16 = 64 (mod 128)
+    // bytes apart, made them collide two ways: 3.4 M of the kernel's 6.0 M shared-store wavefronts, ncu r02)
+    for (int i = threadIdx.x; i < TV * LC; i += NT) {
+      const int l = i / TV, v = i - l * TV;
+      if (v >= nv) continue;
       const int ql = v / HPB, h = h0 + v % HPB;
       const int q = p.q_order ? p.q_order[q0 + ql] : q0 + ql;
       const long long si = (((long long)b * p.Q + q) * p.H + h) * (LC * PC) + l * PC;
