@@ -938,6 +938,11 @@ int run_forward(const msda_b200_desc* desc, const KParams& p, cudaStream_t st) {
 }
 
 // Shared by the plain and the fused backward: zero-fill, main kernel, bf16 conversion.
+// (Measured and dropped, round 2: running the bf16 backward as per-image chains zero-fill -> main kernel -> convert on
+// internal streams forked from the caller's -- main kernels on three low-priority streams, the zero-fills and converts on
+// a high-priority one, each chain in an L2-resident 22 MB slot of the workspace -- to hide the 74 us of the two small
+// kernels under the main kernel. Parity-green, but 1.217 ms per step against 1.210 for the three whole-batch launches
+// (3, 4 or 8 slots alike): the SMs are full of main-kernel blocks, so whatever the small kernels get they take from it.)
 template <bool FUSED>
 int run_backward(const msda_b200_desc* desc, KParams p, void* grad_value, void* workspace, size_t workspace_bytes,
                  bool have_tensors, cudaStream_t st) {
