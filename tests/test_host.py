@@ -80,4 +80,8 @@ def test_collate_batch_matches_reference_collate_fn_schema():
         assert c.dtype == torch.int64 and int(c.max()) < 3
         assert o.dtype == torch.int32 and o.shape == (64, 96)
         assert len(idm) == m.shape[0]
+        # /root/reference/datasets/pheno_bench/dataset.py:85: 255 where there is no instance, ids from 1 elsewhere
+        assert set(o.unique().tolist()) == set(idm) | {255}
+        for j, k in enumerate(sorted(idm)):
+            assert torch.equal(m[j] > 0, o == k)
         assert set(m.unique().tolist()) <= {0.0, 1.0}

@@ -159,10 +159,13 @@ def collate_batch(
 
     ``pixel_values`` (B,3,H,W) float32 stacked; ``mask_labels`` list of (N_i,H,W) float32 binary
     masks; ``class_labels`` list of (N_i,) int64; ``target_sizes`` list of (h,w);
-    ``original_maps`` list of (H,W) int32 instance maps with 0 = background;
+    ``original_maps`` list of (H,W) int32 instance maps, instance ids from 1, 255 = background / ignore as the
+    reference builds them (``/root/reference/datasets/pheno_bench/dataset.py:85``);
     ``id_mappings`` list of {instance_id: class_id}; ``file_names`` list of str.
     Instances are random axis-aligned ellipses ("blobs"), N_i ~ U{1..max_instances}.
     """
+    if not 1 <= max_instances < 255:
+        raise ValueError("max_instances must lie in [1, 254]: 255 marks 'no instance' in original_maps")
     g = torch.Generator()
     g.manual_seed(seed)
     pixel_values = torch.randn(batch, 3, height, width, generator=g)
@@ -171,7 +174,7 @@ def collate_batch(
     mask_labels, class_labels, maps, mappings, names, sizes = [], [], [], [], [], []
     for i in range(batch):
         n = int(torch.randint(1, max_instances + 1, (1,), generator=g))
-        inst = torch.zeros(height, width, dtype=torch.int32)
+        inst = torch.full((height, width), 255, dtype=torch.int32)  # 255 = no instance (reference: np.full(..., 255))
         mapping = {}
         for k in range(1, n + 1):
             cy = float(torch.rand(1, generator=g)) * height
