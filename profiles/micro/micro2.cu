@@ -11,6 +11,9 @@
 // Patterns (W = access width in bytes per lane):
 //   chunk64   4 lanes x 16 B (or 8 x 8 B) cover one random 64-byte run; 8 (4) runs per warp request, each in its own line
 //   chunk64p  as chunk64 but runs come in pairs sharing one 128-byte line (4 lines per request)
+//   chunk64alt  8 runs per request in 8 DIFFERENT lines, lane groups alternating between the lower and the upper half of
+//             their line (what msda_fwd_pair_kernel issues: bank-conflict-free, but eight tags per request)
+//   chunk64same 8 runs in 8 different lines, all in the lower half (what the one-head forward issues)
 //   pair128   8 lanes x 16 B cover 128 contiguous bytes at a random 64-byte-granular offset (two x-adjacent pixels)
 //   line128   8 lanes x 16 B cover one random ALIGNED 128-byte line
 //   linear    lane i reads base + 16 i (fully coalesced)
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(NT) misc_kernel(int iters, int words, unsigned
 
 static unsigned lcg(unsigned& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 
-enum Pattern { CHUNK64, CHUNK64P, PAIR128, LINE128, LINEAR };
+enum Pattern { CHUNK64, CHUNK64P, PAIR128, LINE128, LINEAR, CHUNK64ALT, CHUNK64SAME };
 
 static std::vector<int> make_offsets(Pattern pat, int W, int window) {
   std::vector<int> o(NOFF * NT);
@@ -107,6 +110,13 @@ static std::vector<int> make_offsets(Pattern pat, int W, int window) {
         case PAIR128: v = (grp[t / lanes128] % (window / 64 - 1)) * 64 + (t % lanes128) * W; break;
         case LINE128: v = (grp[t / lanes128] % (window / 128)) * 128 + (t % lanes128) * W; break;
         case LINEAR: v = ((k * NT + t) * W) % window; break;
+        case CHUNK64ALT:
+        case CHUNK64SAME: {
+          const int gi = t / lanes64, per_req = 32 / lanes64, j = gi % per_req, lines = window / 128;
+          const int line = (grp[gi / per_req] + j * (lines / per_req)) % lines;  // per_req distinct lines per request
+          v = line * 128 + (pat == CHUNK64ALT ? (j & 1) * 64 : 0) + (t % lanes64) * W;
+          break;
+        }
       }
       o[k * NT + t] = v;
     }
@@ -167,6 +177,9 @@ int main(int argc, char** argv) {
     run("LDS linear", gather_kernel<4, true>, true, 4, LINEAR, occ);
     run("LDG chunk64 (8 lines/request)", gather_kernel<16, false>, false, 16, CHUNK64, occ);
     run("LDG chunk64p (4 lines/request)", gather_kernel<16, false>, false, 16, CHUNK64P, occ);
+    run("LDG chunk64alt (8 lines, alt. halves)", gather_kernel<16, false>, false, 16, CHUNK64ALT, occ);
+    run("LDG chunk64same (8 lines, one half)", gather_kernel<16, false>, false, 16, CHUNK64SAME, occ);
+    run("LDS chunk64alt (8 lines, alt. halves)", gather_kernel<16, true>, true, 16, CHUNK64ALT, occ);
     run("LDG pair128 (4-8 lines/request)", gather_kernel<16, false>, false, 16, PAIR128, occ);
     run("LDG line128", gather_kernel<16, false>, false, 16, LINE128, occ);
     run("LDG linear", gather_kernel<16, false>, false, 16, LINEAR, occ);
