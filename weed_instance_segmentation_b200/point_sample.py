@@ -83,6 +83,10 @@ class PointSampleFunction(torch.autograd.Function):
         table = ctx.table
         K = coords.shape[1]
         needs = ctx.needs_input_grad[2:]
+        # Peak memory: one fp32 gradient per differentiable source is alive at once (the node returns them together) --
+        # for the batched criterion that is all L decoder layers' (B*Q, h, w) logits, 0.2 GB per layer at batch 8 x 100
+        # queries x 256^2 (2.1 GB for 10 layers), plus a transient low-precision copy per bf16 source. The reference's
+        # per-layer index backward holds one layer at a time; on a 180 GB B200 the single launch is the better trade.
         grads = [torch.zeros(shape, dtype=torch.float32, device=coords.device) if need else None
                  for (shape, _), need in zip(ctx.src_meta, needs)]
         if table.R and K and any(needs):
