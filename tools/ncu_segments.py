@@ -1,7 +1,7 @@
 """Summarise an ncu report of one kernel: headline counters, then instructions / stall samples / shared-memory
 wavefronts per barrier-delimited code segment (ncu --import-source on, read here without a GPU).
 
-    python tools/ncu_segments.py gpurun_out/x.ncu-rep [--kernel REGEX] [--list FIRST LAST]
+    python tools/ncu_segments.py gpurun_out/x.ncu-rep [--kernel REGEX [--skip N]] [--list FIRST LAST]
 """
 import csv
 import io
@@ -10,7 +10,10 @@ import sys
 
 rep = sys.argv[1]
 # optional kernel filter for reports that hold several kernels: --kernel REGEX (first matching launch)
+# (--skip N: the N+1-th matching launch)
 sel = ["-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1], "-c", "1"] if "--kernel" in sys.argv else []
+if "--skip" in sys.argv:
+    sel += ["--launch-skip", sys.argv[sys.argv.index("--skip") + 1]]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", *sel], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, vals = rows[0], rows[2]
