@@ -40,3 +40,30 @@ def test_cpu_baseline_and_reference_arm_lines():
     assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["unit"] == d["unit"]
     assert r["e2e"]["h2d_bytes_per_step"] == 0 and r["e2e"]["d2h_bytes_per_step"] == 0
     assert r["cpu_baseline"]["value"] == r["value"]
+
+
+def test_round2_lines():
+    """Round 2: the N=1 line also carries the reference's function on the same GPU, the config-3 training block and the
+    copy ceiling of the e2e leg; the N=2 / N=8 lines (torchrun) hold the same training block with the NCCL all-reduce."""
+    d = _line("r02_bench_n1.json")
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks",
+                "gpu_reference", "train"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["roofline"]["kernel"] == "msda_bwd_mma_kernel"
+    assert abs(d["value"] - 8 / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    g = d["gpu_reference"]
+    assert g["fp32_ms_per_step"] > d["ms_per_step"] and g["autocast_bf16_ms_per_step"] > d["ms_per_step"]
+    c = d["e2e"]["copy_ceiling"]
+    assert 0 < c["fraction_reached"] <= 1.1 and c["ms_per_step"] > 0
+    t1 = d["train"]
+    assert t1["n_gpus"] == 1 and t1["allreduce_bytes"] == 0 and t1["stock_hf"]["images_per_s"] > 0
+    r = _line("r02_bench_reference_arm.json")
+    assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["config"]["workload"] == d["config"]["workload"]
+    for n in (2, 8):
+        m = _line(f"r02_bench_n{n}.json")
+        t = m["train"]
+        assert m["n_gpus"] == n and t["n_gpus"] == n and t["backend"] == "nccl"
+        assert t["allreduce_bytes"] == 4 * t["params"]  # one fp32 gradient all-reduce per optimiser step
+        # weak scaling of the training step: >= 7/8 of linear against the N=1 line (north star: >= 7x at N=8)
+        assert t["images_per_s"] >= 0.875 * n * t1["images_per_s"]
