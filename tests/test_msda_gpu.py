@@ -164,6 +164,24 @@ def test_sorted_backward_windows(wis, case, dist):
                   safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
 
 
+@pytest.mark.parametrize("variant", ["v1", "v2", "v3"])
+@pytest.mark.parametrize("case", SORTED_CASES[:2] + [CASES[1]], ids=[c[0] for c in SORTED_CASES[:2] + [CASES[1]]])
+def test_every_backward_variant_matches_oracle(wis, monkeypatch, case, variant):
+    """The three selectable bf16 backward kernels -- v1 per-corner reductions (MSDA_B200_FLAG_BWD_V1), v2 pixel-sorted
+    CUDA-core pull (MSDA_B200_FLAG_BWD_V2), v3 group-sorted mma.sync (default) -- each against the oracle."""
+    from weed_instance_segmentation_b200 import functional as F
+    from weed_instance_segmentation_b200.synth import msda_inputs
+    tag, B, shapes, H, D, P, Q = case
+    monkeypatch.setattr(F, "_BWD_V1", variant == "v1")
+    monkeypatch.setattr(F, "_BWD_V2", variant == "v2")
+    for dist in ("init", "adversarial"):
+        x = msda_inputs(B, shapes, num_heads=H, head_dim=D, num_points=P, dist=dist, seed=31, num_queries=Q,
+                        value_dtype=torch.bfloat16)
+        args = (x["value"], shapes, x["sampling_locations"], x["attention_weights"], x["grad_out"])
+        _assert_close(_run(wis, *args), _oracle(*args), BF16_BAR, f"{variant}/{tag}/{dist}",
+                      safe=_kink_safe(x["sampling_locations"].numpy(), shapes))
+
+
 def test_sorted_and_per_corner_backward_agree(wis, monkeypatch):
     """v2 (pixel-sorted) and v1 (per-corner reductions) differ only in fp32 summation order."""
     from weed_instance_segmentation_b200 import functional as F
