@@ -470,6 +470,9 @@ def run_b200(args, rank, world, local_rank):
         "fwd": {"ms": fwd_ms, "frac": ab_fwd / (fwd_ms * 1e-3) / 1e9 / peak},
         "bwd": {"ms": bwd_ms, "frac": ab_bwd / (bwd_ms * 1e-3) / 1e9 / peak},
         "kernels_ms": kern,
+        # dram bytes per launch of each kernel from the committed ncu capture (null when it predates today's sources);
+        # the zero-fill is a memset of the fp32 accumulator
+        "kernels_traffic": {k: recorded_traffic(k) for k in ("fwd", "bwd_main", "bwd_convert")},
     }
 
     # end to end through the public API with host buffers
