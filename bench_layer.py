@@ -92,13 +92,18 @@ def main():
             for _ in range(args.warmup):
                 step()
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                out = step()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / args.steps, out.detach().float(), xin.grad.detach().float()
+            # three timed repeats of `steps`, the median reported: a variant's first repeat occasionally carries one-off
+            # library work (cuBLASLt kernel selection for a new epilogue) that the warm-up did not trigger
+            reps = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    out = step()
+                e1.record()
+                torch.cuda.synchronize()
+                reps.append(e0.elapsed_time(e1) / args.steps)
+            return sorted(reps)[1], out.detach().float(), xin.grad.detach().float()
 
         if patched:
             with wis.installed():

@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 7
+#define MSDA_B200_ABI_VERSION 8
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -178,6 +178,28 @@ int msda_b200_add_layernorm_backward(const float* grad_y /*dev*/, const void* gr
                                      const float* gamma /*dev*/, const float* mean /*dev*/, const float* rstd /*dev*/,
                                      float* grad_sum /*dev*/, void* grad_sum_lowp /*dev|NULL*/, float* grad_gamma /*dev*/,
                                      float* grad_beta /*dev*/, int64_t rows, int32_t channels, void* stream);
+
+/*
+ * The same with the encoder layer's closing clamp folded in (M2F:1062-1065, torch.clamp(y, -clamp, clamp) on the output
+ * of the final LayerNorm while training): y is clamped before it is written (NaN stays NaN, as torch.clamp), and the
+ * backward rebuilds y from x, residual, mean, rstd, gamma and beta and passes the incoming gradient only where
+ * -clamp <= y <= clamp (torch.clamp's backward; false for NaN).  The reference clamps only after a host-side
+ * isfinite().all() check; for finite activations the clamp is the identity, so folding it in removes the clamp, two
+ * compare, one logical-and and one multiply kernel per layer and step without changing a value.  clamp > 0.
+ */
+int msda_b200_add_layernorm_clamp_forward(const void* x /*dev*/, int x_dtype, const void* residual /*dev*/,
+                                          int residual_dtype, const float* gamma /*dev*/, const float* beta /*dev*/,
+                                          float eps, float clamp, float* y /*dev*/, void* y_lowp /*dev|NULL, bfloat16*/,
+                                          float* mean /*dev, rows*/, float* rstd /*dev, rows*/, int64_t rows,
+                                          int32_t channels, void* stream);
+
+int msda_b200_add_layernorm_clamp_backward(const float* grad_y /*dev*/, const void* grad_y_lowp /*dev|NULL, bfloat16*/,
+                                           const void* x /*dev*/, int x_dtype, const void* residual /*dev*/,
+                                           int residual_dtype, const float* gamma /*dev*/, const float* beta /*dev*/,
+                                           float clamp, const float* mean /*dev*/, const float* rstd /*dev*/,
+                                           float* grad_sum /*dev*/, void* grad_sum_lowp /*dev|NULL*/,
+                                           float* grad_gamma /*dev*/, float* grad_beta /*dev*/, int64_t rows,
+                                           int32_t channels, void* stream);
 
 /*
  * Column sum of a contiguous (rows x cols) matrix into float32 -- the bias gradient of a projection

@@ -57,3 +57,47 @@ def test_add_layer_norm_errors():
     y = add_layer_norm(torch.zeros(0, 128, device="cuda"), torch.zeros(0, 128, device="cuda"),
                        torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"))
     assert y.shape == (0, 128)
+
+
+@pytest.mark.parametrize("clamp", [0.75, float(torch.finfo(torch.float32).max - 1000)])
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_add_layer_norm_with_clamp_matches_torch(clamp, xdt):
+    """The encoder layer's closing clamp (M2F:1062-1065) folded into the fused kernels: same values and the same
+    gradients as torch.clamp(F.layer_norm(...)) -- with a small bound (many elements clamped, their gradient masked), at
+    the layer's real bound (identity), and with Inf / NaN planted in the input (NaN stays NaN, no gradient through it)."""
+    from weed_instance_segmentation_b200.layer_norm import add_layer_norm
+    C, rows = 256, 333
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(rows, C, device="cuda", generator=g).to(xdt).requires_grad_(True)
+    r = (2.0 * torch.randn(rows, C, device="cuda", generator=g)).requires_grad_(True)
+    w = (1.0 + 0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    go = torch.randn(rows, C, device="cuda", generator=g)
+    y = add_layer_norm(x, r, w, b, 1e-5, clamp=clamp)
+    y.backward(go)
+    xr, rr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, r, w, b))
+    yr = torch.clamp(F.layer_norm(rr + xr, (C,), wr, br, 1e-5), min=-clamp, max=clamp)
+    yr.backward(go.double())
+    if clamp < 1:
+        assert 0.2 < (yr.detach().abs() >= clamp).double().mean().item() < 0.8  # the bound is active
+        # elements within round-off of the bound may fall on either side in fp32 vs fp64: leave them out of the gradient check
+        pre = F.layer_norm(rr.detach() + xr.detach(), (C,), wr.detach(), br.detach(), 1e-5)
+        safe = ((pre.abs() - clamp).abs() > 1e-4).all(dim=-1, keepdim=True).double()  # whole rows (LayerNorm couples a row)
+        assert safe.mean().item() > 0.3
+    else:
+        safe = torch.ones(rows, 1, device="cuda", dtype=torch.float64)
+    bar_in = 1e-5 if xdt == torch.float32 else 1e-2
+    assert _rel(y.detach(), yr.detach()) <= 1e-5
+    assert _rel(x.grad * safe, xr.grad * safe) <= bar_in and _rel(r.grad * safe, rr.grad * safe) <= 1e-5
+    if clamp > 1:
+        assert _rel(w.grad, wr.grad) <= 2e-5 and _rel(b.grad, br.grad) <= 2e-5
+    # non-finite activations: same treatment as torch.clamp
+    x2 = torch.randn(8, C, device="cuda", generator=g)
+    x2[1, 3], x2[2, 5], x2[4, 7] = float("inf"), float("nan"), -float("inf")
+    r2 = torch.zeros_like(x2)
+    big = float(torch.finfo(torch.float32).max - 1000)
+    got = add_layer_norm(x2, r2, w.detach(), b.detach(), 1e-5, clamp=big)
+    want = torch.clamp(F.layer_norm(x2, (C,), w.detach(), b.detach(), 1e-5), min=-big, max=big)
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    ok = ~torch.isnan(want)
+    assert torch.allclose(got[ok], want[ok], rtol=1e-5, atol=1e-5)

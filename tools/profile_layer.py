@@ -1,4 +1,4 @@
-"""Kernel-level time split of one fused-prologue encoder layer fwd+bwd under bf16 autocast (torch profiler)."""
+"""Kernel-level time split of one B200 encoder layer fwd+bwd under bf16 autocast (torch profiler)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from transformers import Mask2FormerConfig
@@ -12,6 +12,11 @@ torch.manual_seed(0)
 layer = modules.EncoderLayer.from_hf(m2f.Mask2FormerPixelDecoderEncoderLayer(Mask2FormerConfig()).to(dev).train())
 layer.self_attn.assume_no_padding = True
 layer.self_attn.fused_prologue = True
+# the full B200 layer (bench_layer.py's "fused+norm+linear"): fused residual + LayerNorm, projections with the fused
+# bias-gradient reduction, fc1 bias + ReLU epilogue -- PROFILE_LAYER_PLAIN=1 keeps only the fused prologue
+if os.environ.get("PROFILE_LAYER_PLAIN", "0") != "1":
+    layer.fused_norm = True
+    layer.fused_linear = layer.self_attn.fused_linear = True
 S = sum(h * w for h, w in SHAPES); B = 8
 x = torch.randn(B, S, 256, device=dev, requires_grad=True); pos = torch.randn(B, S, 256, device=dev)
 mask = torch.zeros(B, S, dtype=torch.bool, device=dev)
@@ -28,4 +33,4 @@ torch.cuda.synchronize()
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
     for _ in range(5): step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=110))

@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 
 #include "msda_b200.h"
@@ -46,6 +47,8 @@ __device__ __forceinline__ void store4_bf16(void* base, long long idx4, float4 v
   reinterpret_cast<uint2*>(base)[idx4] = o;
 }
 
+__device__ __forceinline__ float clamp_keep_nan(float v, float c) { return v < -c ? -c : (v > c ? c : v); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -59,7 +62,8 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void*
                                                                      const float* __restrict__ beta, float eps,
                                                                      float* __restrict__ y, void* __restrict__ y_lowp,
                                                                      float* __restrict__ mean_out,
-                                                                     float* __restrict__ rstd_out, long long N) {
+                                                                     float* __restrict__ rstd_out, long long N,
+                                                                     float clamp) {
   constexpr int C = CH * 128;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
@@ -90,6 +94,9 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_fwd_kernel(const void*
     o.y = (s[k].y - mean) * rstd * g.y + bt.y;
     o.z = (s[k].z - mean) * rstd * g.z + bt.z;
     o.w = (s[k].w - mean) * rstd * g.w + bt.w;
+    // torch.clamp(y, -clamp, clamp) (M2F:1062-1065; +inf = off): comparisons, not fminf / fmaxf, so that NaN stays NaN
+    o.x = clamp_keep_nan(o.x, clamp); o.y = clamp_keep_nan(o.y, clamp);
+    o.z = clamp_keep_nan(o.z, clamp); o.w = clamp_keep_nan(o.w, clamp);
     reinterpret_cast<float4*>(y)[row * (C / 4) + c4] = o;
     if (y_lowp) store4_bf16(y_lowp, row * (C / 4) + c4, o);  // the next projection's bf16 operand, no separate cast
   }
@@ -109,7 +116,8 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float
                                                                      const float* __restrict__ rstd_in,
                                                                      float* __restrict__ ds, void* __restrict__ ds_lowp,
                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                                     long long N, int rows_per_block) {
+                                                                     long long N, int rows_per_block,
+                                                                     const float* __restrict__ beta, float clamp) {
   constexpr int C = CH * 128;
   __shared__ float4 sg[kRowsPerBlock][CH * 32], sb[kRowsPerBlock][CH * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -135,6 +143,14 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
       xh[k] = make_float4((a.x + b.x - mean) * rstd, (a.y + b.y - mean) * rstd, (a.z + b.z - mean) * rstd,
                           (a.w + b.w - mean) * rstd);
+      if (beta) {  // clamped forward: torch.clamp's backward passes the gradient where -clamp <= y <= clamp (false for NaN)
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        const float y0 = xh[k].x * gm.x + bt.x, y1 = xh[k].y * gm.y + bt.y, y2 = xh[k].z * gm.z + bt.z, y3 = xh[k].w * gm.w + bt.w;
+        d.x = (y0 >= -clamp && y0 <= clamp) ? d.x : 0.f;
+        d.y = (y1 >= -clamp && y1 <= clamp) ? d.y : 0.f;
+        d.z = (y2 >= -clamp && y2 <= clamp) ? d.z : 0.f;
+        d.w = (y3 >= -clamp && y3 <= clamp) ? d.w : 0.f;
+      }
       g[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
       s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
       s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
@@ -178,17 +194,17 @@ __global__ void __launch_bounds__(kThreads) add_layernorm_bwd_kernel(const float
 
 template <int CH>
 int launch_fwd_ch(int xd, int rd, const void* x, const void* r, const float* gamma, const float* beta, float eps, float* y,
-                  void* y_lowp, float* mean, float* rstd, long long N, cudaStream_t st) {
+                  void* y_lowp, float* mean, float* rstd, long long N, float clamp, cudaStream_t st) {
   const unsigned blocks = (unsigned)((N + kRowsPerBlock - 1) / kRowsPerBlock);
   using bf = __nv_bfloat16;
   if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32)
-    add_layernorm_fwd_kernel<bf, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
+    add_layernorm_fwd_kernel<bf, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N, clamp);
   else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32)
-    add_layernorm_fwd_kernel<float, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
+    add_layernorm_fwd_kernel<float, float, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N, clamp);
   else if (xd == MSDA_B200_BF16 && rd == MSDA_B200_BF16)
-    add_layernorm_fwd_kernel<bf, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
+    add_layernorm_fwd_kernel<bf, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N, clamp);
   else
-    add_layernorm_fwd_kernel<float, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N);
+    add_layernorm_fwd_kernel<float, bf, CH><<<blocks, kThreads, 0, st>>>(x, r, gamma, beta, eps, y, y_lowp, mean, rstd, N, clamp);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
 }
@@ -196,7 +212,8 @@ int launch_fwd_ch(int xd, int rd, const void* x, const void* r, const float* gam
 template <int CH>
 int launch_bwd_ch(int xd, int rd, const float* dy, const void* dy_lowp, const void* x, const void* r, const float* gamma,
                   const float* mean,
-                  const float* rstd, float* ds, void* ds_lowp, float* dgamma, float* dbeta, long long N, cudaStream_t st) {
+                  const float* rstd, float* ds, void* ds_lowp, float* dgamma, float* dbeta, long long N,
+                  const float* beta, float clamp, cudaStream_t st) {
   // ~4 blocks per SM; each block walks a contiguous range of rows so the gamma/beta partials stay in registers
   long long blocks = 148 * 4;
   if (blocks > (N + kRowsPerBlock - 1) / kRowsPerBlock) blocks = (N + kRowsPerBlock - 1) / kRowsPerBlock;
@@ -207,10 +224,10 @@ int launch_bwd_ch(int xd, int rd, const float* dy, const void* dy_lowp, const vo
   do {                                                                                                            \
     if (ds_lowp)                                                                                                  \
       add_layernorm_bwd_kernel<XT, RT, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(                          \
-          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                   \
+          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block, beta, clamp);                   \
     else                                                                                                          \
       add_layernorm_bwd_kernel<XT, RT, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(                         \
-          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block);                   \
+          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block, beta, clamp);                   \
   } while (0)
   if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32) MSDA_LN_BWD(bf, float);
   else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32) MSDA_LN_BWD(float, float);
@@ -227,29 +244,33 @@ bool bad_dtype(int d) { return d != MSDA_B200_F32 && d != MSDA_B200_BF16; }
 
 extern "C" {
 
-int msda_b200_add_layernorm_forward(const void* x, int x_dtype, const void* residual, int residual_dtype,
-                                    const float* gamma, const float* beta, float eps, float* y, void* y_lowp, float* mean,
-                                    float* rstd, int64_t rows, int32_t channels, void* stream) {
+// clamp: +inf = plain LayerNorm; finite = torch.clamp(y, -clamp, clamp) applied to the output (M2F:1062-1065)
+static int add_layernorm_forward_impl(const void* x, int x_dtype, const void* residual, int residual_dtype,
+                                      const float* gamma, const float* beta, float eps, float* y, void* y_lowp, float* mean,
+                                      float* rstd, int64_t rows, int32_t channels, float clamp, void* stream) {
   if (rows < 0 || channels <= 0 || channels % 128 != 0 || channels > kMaxC)
     return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: channels must be a multiple of 128, at most 512");
   if (bad_dtype(x_dtype) || bad_dtype(residual_dtype))
     return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: dtype must be 0 (f32) or 1 (bf16)");
+  if (!(clamp > 0.f)) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm: clamp must be positive");
   if (rows == 0) return MSDA_B200_OK;
   if (!x || !residual || !gamma || !beta || !y || !mean || !rstd)
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_forward: NULL tensor pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (channels / 128) {
-    case 1: return launch_fwd_ch<1>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
-    case 2: return launch_fwd_ch<2>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
-    case 4: return launch_fwd_ch<4>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, st);
+    case 1: return launch_fwd_ch<1>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, clamp, st);
+    case 2: return launch_fwd_ch<2>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, clamp, st);
+    case 4: return launch_fwd_ch<4>(x_dtype, residual_dtype, x, residual, gamma, beta, eps, y, y_lowp, mean, rstd, rows, clamp, st);
   }
   return MSDA_B200_ERR_UNSUPPORTED;
 }
 
-int msda_b200_add_layernorm_backward(const float* grad_y, const void* grad_y_lowp, const void* x, int x_dtype, const void* residual,
-                                     int residual_dtype, const float* gamma, const float* mean, const float* rstd,
-                                     float* grad_sum, void* grad_sum_lowp, float* grad_gamma, float* grad_beta,
-                                     int64_t rows, int32_t channels, void* stream) {
+// beta == NULL: plain LayerNorm backward; else the backward of the clamped forward (needs beta to rebuild y)
+static int add_layernorm_backward_impl(const float* grad_y, const void* grad_y_lowp, const void* x, int x_dtype,
+                                       const void* residual, int residual_dtype, const float* gamma, const float* beta,
+                                       float clamp, const float* mean, const float* rstd, float* grad_sum,
+                                       void* grad_sum_lowp, float* grad_gamma, float* grad_beta, int64_t rows,
+                                       int32_t channels, void* stream) {
   if (rows < 0 || channels <= 0 || channels % 128 != 0 || channels > kMaxC)
     return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "add_layernorm: channels must be a multiple of 128, at most 512");
   if (bad_dtype(x_dtype) || bad_dtype(residual_dtype))
@@ -263,11 +284,45 @@ int msda_b200_add_layernorm_backward(const float* grad_y, const void* grad_y_low
   if (!grad_y || !x || !residual || !gamma || !mean || !rstd || !grad_sum)
     return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_backward: NULL tensor pointer");
   switch (channels / 128) {
-    case 1: return launch_bwd_ch<1>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
-    case 2: return launch_bwd_ch<2>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
-    case 4: return launch_bwd_ch<4>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, st);
+    case 1: return launch_bwd_ch<1>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, beta, clamp, st);
+    case 2: return launch_bwd_ch<2>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, beta, clamp, st);
+    case 4: return launch_bwd_ch<4>(x_dtype, residual_dtype, grad_y, grad_y_lowp, x, residual, gamma, mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, beta, clamp, st);
   }
   return MSDA_B200_ERR_UNSUPPORTED;
+}
+
+int msda_b200_add_layernorm_forward(const void* x, int x_dtype, const void* residual, int residual_dtype,
+                                    const float* gamma, const float* beta, float eps, float* y, void* y_lowp, float* mean,
+                                    float* rstd, int64_t rows, int32_t channels, void* stream) {
+  return add_layernorm_forward_impl(x, x_dtype, residual, residual_dtype, gamma, beta, eps, y, y_lowp, mean, rstd, rows,
+                                    channels, INFINITY, stream);
+}
+
+int msda_b200_add_layernorm_backward(const float* grad_y, const void* grad_y_lowp, const void* x, int x_dtype, const void* residual,
+                                     int residual_dtype, const float* gamma, const float* mean, const float* rstd,
+                                     float* grad_sum, void* grad_sum_lowp, float* grad_gamma, float* grad_beta,
+                                     int64_t rows, int32_t channels, void* stream) {
+  return add_layernorm_backward_impl(grad_y, grad_y_lowp, x, x_dtype, residual, residual_dtype, gamma, nullptr, INFINITY,
+                                     mean, rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, channels, stream);
+}
+
+int msda_b200_add_layernorm_clamp_forward(const void* x, int x_dtype, const void* residual, int residual_dtype,
+                                          const float* gamma, const float* beta, float eps, float clamp, float* y,
+                                          void* y_lowp, float* mean, float* rstd, int64_t rows, int32_t channels,
+                                          void* stream) {
+  return add_layernorm_forward_impl(x, x_dtype, residual, residual_dtype, gamma, beta, eps, y, y_lowp, mean, rstd, rows,
+                                    channels, clamp, stream);
+}
+
+int msda_b200_add_layernorm_clamp_backward(const float* grad_y, const void* grad_y_lowp, const void* x, int x_dtype,
+                                           const void* residual, int residual_dtype, const float* gamma, const float* beta,
+                                           float clamp, const float* mean, const float* rstd, float* grad_sum,
+                                           void* grad_sum_lowp, float* grad_gamma, float* grad_beta, int64_t rows,
+                                           int32_t channels, void* stream) {
+  if (!beta) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm_clamp_backward: beta is NULL");
+  if (!(clamp > 0.f)) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "add_layernorm: clamp must be positive");
+  return add_layernorm_backward_impl(grad_y, grad_y_lowp, x, x_dtype, residual, residual_dtype, gamma, beta, clamp, mean,
+                                     rstd, grad_sum, grad_sum_lowp, grad_gamma, grad_beta, rows, channels, stream);
 }
 
 }  // extern "C"

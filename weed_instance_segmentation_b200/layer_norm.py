@@ -20,7 +20,7 @@ def _ptr(t):
 
 class AddLayerNormFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, eps, also_lowp=False):
+    def forward(ctx, x, residual, weight, bias, eps, also_lowp=False, clamp=None):
         lib = _cabi.load()
         ctx.set_materialize_grads(False)
         C = x.shape[-1]
@@ -33,10 +33,17 @@ class AddLayerNormFunction(torch.autograd.Function):
         y_lowp = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device) if also_lowp else None
         with torch.cuda.device(xc.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _cabi.check(lib.msda_b200_add_layernorm_forward(_ptr(xc), _DTYPE_CODE[xc.dtype], _ptr(rc), _DTYPE_CODE[rc.dtype],
-                                                            _ptr(w), _ptr(b), float(eps), _ptr(y), _ptr(y_lowp), _ptr(mean),
-                                                            _ptr(rstd), rows, C, stream))
-        ctx.save_for_backward(xc, rc, w, mean, rstd)
+            if clamp is None:
+                _cabi.check(lib.msda_b200_add_layernorm_forward(_ptr(xc), _DTYPE_CODE[xc.dtype], _ptr(rc),
+                                                                _DTYPE_CODE[rc.dtype], _ptr(w), _ptr(b), float(eps), _ptr(y),
+                                                                _ptr(y_lowp), _ptr(mean), _ptr(rstd), rows, C, stream))
+            else:
+                _cabi.check(lib.msda_b200_add_layernorm_clamp_forward(_ptr(xc), _DTYPE_CODE[xc.dtype], _ptr(rc),
+                                                                      _DTYPE_CODE[rc.dtype], _ptr(w), _ptr(b), float(eps),
+                                                                      float(clamp), _ptr(y), _ptr(y_lowp), _ptr(mean),
+                                                                      _ptr(rstd), rows, C, stream))
+        ctx.clamp = clamp
+        ctx.save_for_backward(xc, rc, w, mean, rstd, *((b,) if clamp is not None else ()))
         ctx.param_dtypes = (weight.dtype, bias.dtype)
         return (y, y_lowp) if also_lowp else y
 
@@ -44,7 +51,7 @@ class AddLayerNormFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_y, grad_y_lowp=None):
         lib = _cabi.load()
-        x, r, w, mean, rstd = ctx.saved_tensors
+        x, r, w, mean, rstd = ctx.saved_tensors[:5]
         C = x.shape[-1]
         rows = x.numel() // C
         if grad_y is None:  # only the bfloat16 copy was used downstream
@@ -58,22 +65,31 @@ class AddLayerNormFunction(torch.autograd.Function):
         gb = torch.empty(C, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _cabi.check(lib.msda_b200_add_layernorm_backward(_ptr(gy), _ptr(gyl), _ptr(x), _DTYPE_CODE[x.dtype], _ptr(r),
-                                                             _DTYPE_CODE[r.dtype], _ptr(w), _ptr(mean), _ptr(rstd), _ptr(ds),
-                                                             _ptr(ds_lowp), _ptr(gw), _ptr(gb), rows, C, stream))
+            if ctx.clamp is None:
+                _cabi.check(lib.msda_b200_add_layernorm_backward(_ptr(gy), _ptr(gyl), _ptr(x), _DTYPE_CODE[x.dtype], _ptr(r),
+                                                                 _DTYPE_CODE[r.dtype], _ptr(w), _ptr(mean), _ptr(rstd),
+                                                                 _ptr(ds), _ptr(ds_lowp), _ptr(gw), _ptr(gb), rows, C, stream))
+            else:
+                _cabi.check(lib.msda_b200_add_layernorm_clamp_backward(
+                    _ptr(gy), _ptr(gyl), _ptr(x), _DTYPE_CODE[x.dtype], _ptr(r), _DTYPE_CODE[r.dtype], _ptr(w),
+                    _ptr(ctx.saved_tensors[5]), float(ctx.clamp), _ptr(mean), _ptr(rstd), _ptr(ds), _ptr(ds_lowp), _ptr(gw),
+                    _ptr(gb), rows, C, stream))
         gx = ds_lowp if x.dtype == torch.bfloat16 else ds
         gr = ds_lowp if r.dtype == torch.bfloat16 else ds
         wd, bd = ctx.param_dtypes
-        return gx, gr, gw.to(wd), gb.to(bd), None, None
+        return gx, gr, gw.to(wd), gb.to(bd), None, None, None
 
 
 def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
-                   eps: float = 1e-5, also_lowp: bool = False):
+                   eps: float = 1e-5, also_lowp: bool = False, clamp: float | None = None):
     """``F.layer_norm(residual + x, (C,), weight, bias, eps)`` in one kernel; float32 output.
 
     ``also_lowp``: additionally return the same values rounded to bfloat16 (``(y, y_bf16)``): the operand of the
     projection that follows under autocast, written by the same kernel instead of a separate cast; the gradient that
     returns through it is added inside the backward kernel.
+
+    ``clamp``: fold ``torch.clamp(y, -clamp, clamp)`` (the encoder layer's closing clamp, M2F:1062-1065) into the same
+    kernels, forward and backward, with torch.clamp's semantics (NaN stays NaN; no gradient where y is out of range).
 
     ``x`` and ``residual``: same shape ``(..., C)``, float32 or bfloat16, CUDA; ``C`` a multiple of 128, at most 512.
     """
@@ -86,4 +102,6 @@ def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor
     C = x.shape[-1]
     if weight.numel() != C or bias.numel() != C:
         raise ValueError("add_layer_norm: weight / bias must have C elements")
-    return AddLayerNormFunction.apply(x, residual, weight, bias, eps, also_lowp)
+    if clamp is not None and not clamp > 0:
+        raise ValueError("add_layer_norm: clamp must be positive")
+    return AddLayerNormFunction.apply(x, residual, weight, bias, eps, also_lowp, clamp)

@@ -181,17 +181,23 @@ class EncoderLayer(nn.Module):
     def _proj(self, layer: nn.Linear, x):
         return _fused_linear(x, layer.weight, layer.bias) if self.fused_linear else layer(x)
 
-    def _add_norm(self, branch, residual, norm, also_lowp=False):
+    def _add_norm(self, branch, residual, norm, also_lowp=False, clamp=False):
         """``norm(residual + branch)`` (M2F:1049-1050, 1058-1059); one fused kernel when ``fused_norm`` is set.
-        ``also_lowp``: return ``(y, y_bf16_or_None)`` -- the bfloat16 copy comes out of the same kernel."""
+        ``also_lowp``: return ``(y, y_bf16_or_None)`` -- the bfloat16 copy comes out of the same kernel.
+        ``clamp``: also apply the layer's closing ``torch.clamp(y, -c, c)``, ``c = finfo(y.dtype).max - 1000``
+        (M2F:1062-1065) -- inside the fused kernels when they run."""
         ok = (self.fused_norm and branch.is_cuda and branch.shape[-1] % 128 == 0 and branch.shape[-1] <= 512
               and branch.dtype in (torch.float32, torch.bfloat16) and residual.dtype in (torch.float32, torch.bfloat16)
               and (torch.is_autocast_enabled() or (branch.dtype == residual.dtype == torch.float32)))
         if ok:
             lowp = also_lowp and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
-            res = add_layer_norm(branch, residual, norm.weight, norm.bias, norm.eps, also_lowp=lowp)
+            c = float(torch.finfo(torch.float32).max - 1000) if clamp else None  # the fused kernels return float32
+            res = add_layer_norm(branch, residual, norm.weight, norm.bias, norm.eps, also_lowp=lowp, clamp=c)
             return (res if lowp else (res, None)) if also_lowp else res
         y = norm(residual + branch)
+        if clamp:
+            c = torch.finfo(y.dtype).max - 1000
+            y = torch.clamp(y, min=-c, max=c)
         return (y, None) if also_lowp else y
 
     def forward(
@@ -229,15 +235,11 @@ class EncoderLayer(nn.Module):
         hidden_states = F.dropout(hidden_states, p=self.activation_dropout, training=self.training)
         hidden_states = self._proj(self.fc2, hidden_states)
         hidden_states = F.dropout(hidden_states, p=self.dropout, training=self.training)
-        hidden_states = self._add_norm(hidden_states, residual, self.final_layer_norm)
-
-        if self.training:
-            # The reference clamps only `if not torch.isfinite(hidden_states).all()` (M2F:1062-1065), a
-            # device->host sync per layer per step. The clamp bounds are finfo.max - 1000, so for finite
-            # inputs it is the identity and NaN passes through unchanged: applying it unconditionally
-            # gives the same tensor without stalling the stream.
-            clamp_value = torch.finfo(hidden_states.dtype).max - 1000
-            hidden_states = torch.clamp(hidden_states, min=-clamp_value, max=clamp_value)
+        # The reference clamps only `if not torch.isfinite(hidden_states).all()` (M2F:1062-1065), a device->host sync
+        # per layer per step. The clamp bounds are finfo.max - 1000, so for finite inputs it is the identity and NaN
+        # passes through unchanged: applying it unconditionally gives the same tensor without stalling the stream, and
+        # the fused LayerNorm kernels apply it (and its backward mask) in place of five elementwise kernels.
+        hidden_states = self._add_norm(hidden_states, residual, self.final_layer_norm, clamp=self.training)
 
         outputs = (hidden_states,)
         if output_attentions:
