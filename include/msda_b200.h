@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 8
+#define MSDA_B200_ABI_VERSION 9
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -200,6 +200,21 @@ int msda_b200_add_layernorm_clamp_backward(const float* grad_y /*dev*/, const vo
                                            float* grad_sum /*dev*/, void* grad_sum_lowp /*dev|NULL*/,
                                            float* grad_gamma /*dev*/, float* grad_beta /*dev*/, int64_t rows,
                                            int32_t channels, void* stream);
+
+/*
+ * Operands of the attention module under bfloat16 autocast (M2F:936-937, 947, 952-956) in one pass:
+ *   query_bf16 = bfloat16(hidden + pos)  (read by the sampling_offsets / attention_weights projections),
+ *   value_bf16 = bfloat16(hidden)        (read by value_proj),
+ * with the roundings of the stock sequence (fp32 add, one round-to-nearest-even).  hidden / pos: float32, `elements`
+ * each (a multiple of 8), contiguous.  Backward: grad_hidden = f32(grad_query) + f32(grad_value), grad_pos (optional) =
+ * f32(grad_query); either incoming gradient may be NULL (= zero).
+ */
+int msda_b200_query_value_cast_forward(const float* hidden /*dev*/, const float* pos /*dev*/, void* query_bf16 /*dev*/,
+                                       void* value_bf16 /*dev*/, int64_t elements, void* stream);
+
+int msda_b200_query_value_cast_backward(const void* grad_query_bf16 /*dev|NULL*/, const void* grad_value_bf16 /*dev|NULL*/,
+                                        float* grad_hidden /*dev*/, float* grad_pos /*dev|NULL*/, int64_t elements,
+                                        void* stream);
 
 /*
  * Column sum of a contiguous (rows x cols) matrix into float32 -- the bias gradient of a projection

@@ -60,3 +60,31 @@ def test_column_sum_errors():
     with pytest.raises(MSDAError):
         column_sum(torch.zeros(4, 12, device="cuda", dtype=torch.bfloat16))  # 12 columns: not a multiple of 8
     assert column_sum(torch.zeros(0, 16, device="cuda")).abs().sum().item() == 0
+
+
+def test_query_value_cast_is_the_stock_sequence():
+    """bfloat16(hidden + pos) and bfloat16(hidden) from one kernel: bit-identical to the fp32 add + two casts of the
+    stock module under autocast (M2F:936-937, 947), and so are the gradients (two casts + an add)."""
+    from weed_instance_segmentation_b200.linear import query_value_cast
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape in ((2, 333, 256), (1, 8), (3, 0, 256)):
+        h = torch.randn(shape, device="cuda", generator=g).requires_grad_(True)
+        p = (0.3 * torch.randn(shape, device="cuda", generator=g)).requires_grad_(True)
+        q, v = query_value_cast(h, p)
+        assert q.dtype == v.dtype == torch.bfloat16
+        assert torch.equal(q, (h + p).to(torch.bfloat16)) and torch.equal(v, h.to(torch.bfloat16))
+        gq = torch.randn(shape, device="cuda", generator=g).to(torch.bfloat16)
+        gv = torch.randn(shape, device="cuda", generator=g).to(torch.bfloat16)
+        torch.autograd.backward([q, v], [gq, gv])
+        assert torch.equal(h.grad, gq.float() + gv.float()) and torch.equal(p.grad, gq.float())
+        # only one of the two operands used downstream; pos without gradient
+        h2 = h.detach().clone().requires_grad_(True)
+        q2, v2 = query_value_cast(h2, p.detach())
+        v2.backward(gv)
+        assert torch.equal(h2.grad, gv.float())
+    with pytest.raises(ValueError):
+        query_value_cast(torch.zeros(4, 8, device="cuda"), torch.zeros(4, 16, device="cuda"))
+    with pytest.raises(TypeError):
+        query_value_cast(torch.zeros(4, 8, device="cuda", dtype=torch.bfloat16), torch.zeros(4, 8, device="cuda"))
+    with pytest.raises(RuntimeError):
+        query_value_cast(torch.zeros(4, 8), torch.zeros(4, 8))

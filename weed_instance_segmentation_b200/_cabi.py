@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_LEVELS = 8
 F32, BF16, U8 = 0, 1, 2
 FLAG_PROFILE = 1
@@ -35,6 +35,8 @@ EXPORTS = (
     "msda_b200_add_layernorm_backward",
     "msda_b200_add_layernorm_clamp_forward",
     "msda_b200_add_layernorm_clamp_backward",
+    "msda_b200_query_value_cast_forward",
+    "msda_b200_query_value_cast_backward",
     "msda_b200_column_sum",
     "msda_b200_groupnorm_to_rows_forward",
     "msda_b200_groupnorm_to_rows_backward",
@@ -114,6 +116,10 @@ def load() -> ctypes.CDLL:
     lib.msda_b200_add_layernorm_clamp_backward.restype = ctypes.c_int
     lib.msda_b200_add_layernorm_clamp_backward.argtypes = [vp, vp, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, ctypes.c_float,
                                                            vp, vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    lib.msda_b200_query_value_cast_forward.restype = ctypes.c_int
+    lib.msda_b200_query_value_cast_forward.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp]
+    lib.msda_b200_query_value_cast_backward.restype = ctypes.c_int
+    lib.msda_b200_query_value_cast_backward.argtypes = [vp, vp, vp, vp, ctypes.c_int64, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_groupnorm_to_rows_forward.restype = ctypes.c_int

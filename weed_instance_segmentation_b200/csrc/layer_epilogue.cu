@@ -417,3 +417,96 @@ extern "C" int msda_b200_column_sum(const void* matrix, int dtype, float* out, i
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Query / value operands of the attention module under bf16 autocast (M2F:936-937, 947, 952-956):
+//   query = bfloat16(hidden + pos)   -- what the sampling_offsets / attention_weights projections read
+//   value = bfloat16(hidden)         -- what value_proj reads
+// Stock PyTorch runs an fp32 add (read 2, write 1 tensor) and two cast kernels (read 1, write 1/2 each); one pass here
+// reads hidden and pos once and writes the two bf16 operands. Backward: grad_hidden = f32(grad_query) + f32(grad_value),
+// grad_pos = f32(grad_query), again one pass instead of two casts and an add. Same roundings as the stock sequence
+// (fp32 add, one round-to-nearest-even to bfloat16; bfloat16 -> fp32 is exact).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint4 pack8_bf16(const float4& a, const float4& b) {
+  const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 o;
+  o.x = *reinterpret_cast<const unsigned*>(&p0); o.y = *reinterpret_cast<const unsigned*>(&p1);
+  o.z = *reinterpret_cast<const unsigned*>(&p2); o.w = *reinterpret_cast<const unsigned*>(&p3);
+  return o;
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& v, float4& a, float4& b) {
+  a = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                  __uint_as_float(v.y & 0xffff0000u));
+  b = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16),
+                  __uint_as_float(v.w & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(256) qv_cast_fwd_kernel(const float4* __restrict__ hidden, const float4* __restrict__ pos,
+                                                          uint4* __restrict__ query, uint4* __restrict__ value,
+                                                          long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 h0 = __ldg(hidden + 2 * i), h1 = __ldg(hidden + 2 * i + 1);
+    const float4 p0 = __ldg(pos + 2 * i), p1 = __ldg(pos + 2 * i + 1);
+    value[i] = pack8_bf16(h0, h1);
+    query[i] = pack8_bf16(make_float4(h0.x + p0.x, h0.y + p0.y, h0.z + p0.z, h0.w + p0.w),
+                          make_float4(h1.x + p1.x, h1.y + p1.y, h1.z + p1.z, h1.w + p1.w));
+  }
+}
+
+// grad_query / grad_value may be NULL (no gradient arrived through that operand): treated as zero
+__global__ void __launch_bounds__(256) qv_cast_bwd_kernel(const uint4* __restrict__ grad_query,
+                                                          const uint4* __restrict__ grad_value,
+                                                          float4* __restrict__ grad_hidden, float4* __restrict__ grad_pos,
+                                                          long long n8) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float4 q0 = z, q1 = z, v0 = z, v1 = z;
+    if (grad_query) unpack8_bf16(__ldg(grad_query + i), q0, q1);
+    if (grad_value) unpack8_bf16(__ldg(grad_value + i), v0, v1);
+    grad_hidden[2 * i] = make_float4(q0.x + v0.x, q0.y + v0.y, q0.z + v0.z, q0.w + v0.w);
+    grad_hidden[2 * i + 1] = make_float4(q1.x + v1.x, q1.y + v1.y, q1.z + v1.z, q1.w + v1.w);
+    if (grad_pos) {
+      grad_pos[2 * i] = q0;
+      grad_pos[2 * i + 1] = q1;
+    }
+  }
+}
+
+int qv_blocks(long long n8) {
+  const long long want = (n8 + 255) / 256;
+  return (int)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+}
+
+}  // namespace
+
+extern "C" int msda_b200_query_value_cast_forward(const float* hidden, const float* pos, void* query_bf16, void* value_bf16,
+                                                  int64_t elements, void* stream) {
+  if (elements < 0 || elements % 8 != 0)
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "query_value_cast: element count must be a multiple of 8");
+  if (elements == 0) return MSDA_B200_OK;
+  if (!hidden || !pos || !query_bf16 || !value_bf16)
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "query_value_cast_forward: NULL tensor pointer");
+  const long long n8 = elements / 8;
+  qv_cast_fwd_kernel<<<qv_blocks(n8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(hidden), reinterpret_cast<const float4*>(pos), reinterpret_cast<uint4*>(query_bf16),
+      reinterpret_cast<uint4*>(value_bf16), n8);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
+}
+
+extern "C" int msda_b200_query_value_cast_backward(const void* grad_query_bf16, const void* grad_value_bf16,
+                                                   float* grad_hidden, float* grad_pos, int64_t elements, void* stream) {
+  if (elements < 0 || elements % 8 != 0)
+    return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "query_value_cast: element count must be a multiple of 8");
+  if (elements == 0) return MSDA_B200_OK;
+  if (!grad_hidden) return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "query_value_cast_backward: grad_hidden is NULL");
+  const long long n8 = elements / 8;
+  qv_cast_bwd_kernel<<<qv_blocks(n8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(grad_query_bf16), reinterpret_cast<const uint4*>(grad_value_bf16),
+      reinterpret_cast<float4*>(grad_hidden), reinterpret_cast<float4*>(grad_pos), n8);
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
+}

@@ -118,3 +118,55 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.T
     if not ok:
         return F.linear(x, weight, bias)
     return LinearFunction.apply(x, weight, bias)
+
+
+class QueryValueCastFunction(torch.autograd.Function):
+    """``(bfloat16(hidden + pos), bfloat16(hidden))`` in one pass (``msda_b200_query_value_cast_*``)."""
+
+    @staticmethod
+    def forward(ctx, hidden, pos):
+        lib = _cabi.load()
+        ctx.set_materialize_grads(False)
+        h, p = hidden.contiguous(), pos.contiguous()
+        q = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device)
+        v = torch.empty(h.shape, dtype=torch.bfloat16, device=h.device)
+        with torch.cuda.device(h.device):
+            _cabi.check(lib.msda_b200_query_value_cast_forward(h.data_ptr() if h.numel() else None,
+                                                               p.data_ptr() if p.numel() else None,
+                                                               q.data_ptr() if q.numel() else None,
+                                                               v.data_ptr() if v.numel() else None, h.numel(),
+                                                               torch.cuda.current_stream().cuda_stream))
+        ctx.shape, ctx.device = h.shape, h.device
+        return q, v
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_q, grad_v):
+        lib = _cabi.load()
+        need_h, need_p = ctx.needs_input_grad
+        if not (need_h or need_p):
+            return None, None
+        gq = grad_q.to(torch.bfloat16).contiguous() if grad_q is not None else None
+        gv = grad_v.to(torch.bfloat16).contiguous() if grad_v is not None else None
+        gh = torch.empty(ctx.shape, dtype=torch.float32, device=ctx.device)
+        gp = torch.empty(ctx.shape, dtype=torch.float32, device=ctx.device) if need_p else None
+        ptr = lambda t: t.data_ptr() if t is not None and t.numel() else None  # noqa: E731
+        with torch.cuda.device(ctx.device):
+            _cabi.check(lib.msda_b200_query_value_cast_backward(ptr(gq), ptr(gv), ptr(gh), ptr(gp), gh.numel(),
+                                                                torch.cuda.current_stream().cuda_stream))
+        return (gh if need_h else None), gp
+
+
+def query_value_cast(hidden: torch.Tensor, pos: torch.Tensor):
+    """The attention module's two bfloat16 operands from the float32 hidden state and position embedding
+    (M2F:936-937, 947): ``(bfloat16(hidden + pos), bfloat16(hidden))``, one kernel per direction instead of an fp32 add and
+    two casts (forward) / two casts and an add (backward). Same values as the stock sequence."""
+    if not (hidden.is_cuda and pos.is_cuda):
+        raise RuntimeError("query_value_cast: tensors must live on a CUDA device (this package has no CPU fallback)")
+    if hidden.dtype != torch.float32 or pos.dtype != torch.float32:
+        raise TypeError("query_value_cast: float32 inputs only")
+    if hidden.shape != pos.shape:
+        raise ValueError(f"query_value_cast: hidden {tuple(hidden.shape)} and pos {tuple(pos.shape)} differ")
+    if hidden.numel() % 8:
+        raise ValueError("query_value_cast: the element count must be a multiple of 8")
+    return QueryValueCastFunction.apply(hidden, pos)

@@ -25,6 +25,7 @@ from .fused import ms_deform_attn_fused
 from .layer_norm import add_layer_norm
 from .linear import linear as _fused_linear
 from .linear import linear_relu as _fused_linear_relu
+from .linear import query_value_cast as _query_value_cast
 
 
 class MSDeformAttn(nn.Module):
@@ -90,7 +91,16 @@ class MSDeformAttn(nn.Module):
         level_start_index=None,
         output_attentions: bool = False,
     ):
-        if position_embeddings is not None:
+        # Self-attention under bfloat16 autocast (the pixel decoder): the projections read bfloat16(hidden + pos) and
+        # bfloat16(hidden) -- one kernel writes both (linear.query_value_cast) instead of an fp32 add and two casts.
+        value_in = encoder_hidden_states
+        if (self.fused_linear and position_embeddings is not None and encoder_hidden_states is hidden_states
+                and hidden_states.is_cuda and hidden_states.dtype == torch.float32
+                and position_embeddings.dtype == torch.float32 and position_embeddings.shape == hidden_states.shape
+                and hidden_states.numel() % 8 == 0 and torch.is_autocast_enabled("cuda")
+                and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            hidden_states, value_in = _query_value_cast(hidden_states, position_embeddings)
+        elif position_embeddings is not None:
             hidden_states = self.with_pos_embed(hidden_states, position_embeddings)
         batch_size, num_queries, _ = hidden_states.shape
         batch_size, sequence_length, _ = encoder_hidden_states.shape
@@ -104,7 +114,7 @@ class MSDeformAttn(nn.Module):
         if torch.is_autocast_enabled("cuda") and hidden_states.is_cuda and hidden_states.dtype == torch.float32:
             # both query projections read `hidden_states`: cast it to the autocast dtype ONCE (F.linear would do it twice)
             hidden_states = hidden_states.to(torch.get_autocast_dtype("cuda"))
-        value = self._proj(self.value_proj, encoder_hidden_states)
+        value = self._proj(self.value_proj, value_in)
         if attention_mask is not None and not self.assume_no_padding:
             value = value.masked_fill(attention_mask[..., None], float(0))
         value = value.view(batch_size, sequence_length, H, self.d_model // H)
