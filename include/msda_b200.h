@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 9
+#define MSDA_B200_ABI_VERSION 10
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -215,6 +215,27 @@ int msda_b200_query_value_cast_forward(const float* hidden /*dev*/, const float*
 int msda_b200_query_value_cast_backward(const void* grad_query_bf16 /*dev|NULL*/, const void* grad_value_bf16 /*dev|NULL*/,
                                         float* grad_hidden /*dev*/, float* grad_pos /*dev|NULL*/, int64_t elements,
                                         void* stream);
+
+/*
+ * float32 projections on the bf16 tensor cores (csrc/gemm_f32.cu): the row-major products of F.linear and its backward,
+ *   y[rows, out] = x[rows, in] . weight[out, in]^T (+ bias[out]) (+ ReLU when `relu` != 0; needs a bias),
+ *   grad_x[rows, in] = grad_y[rows, out] . weight[out, in],     grad_weight[out, in] = grad_y^T . x,
+ * as cuBLASLt GEMMs with CUBLAS_COMPUTE_32F_EMULATED_16BFX9 (every float32 operand split into three bfloat16 terms, nine
+ * products accumulated in float32: at least SGEMM's accuracy, ~2x its speed on B200).  The CUDA toolkit's cuBLASLt
+ * (>= 12.9) is opened at first use; msda_b200_linear_f32_available() returns 1 when it is there and accepts the compute
+ * type, else 0 (the calls then return MSDA_B200_ERR_UNSUPPORTED).  `workspace` (device, caller-owned, may be NULL with
+ * 0 bytes) bounds what cuBLASLt may use for split-K; 32-64 MB is plenty.  All tensors contiguous float32 on the device.
+ */
+int msda_b200_linear_f32_available(void);
+int msda_b200_linear_f32_forward(const float* x /*dev*/, const float* weight /*dev*/, const float* bias /*dev|NULL*/,
+                                 int relu, float* y /*dev*/, int64_t rows, int32_t out_features, int32_t in_features,
+                                 void* workspace /*dev|NULL*/, size_t workspace_bytes, void* stream);
+int msda_b200_linear_f32_grad_input(const float* grad_y /*dev*/, const float* weight /*dev*/, float* grad_x /*dev*/,
+                                    int64_t rows, int32_t out_features, int32_t in_features, void* workspace /*dev|NULL*/,
+                                    size_t workspace_bytes, void* stream);
+int msda_b200_linear_f32_grad_weight(const float* grad_y /*dev*/, const float* x /*dev*/, float* grad_weight /*dev*/,
+                                     int64_t rows, int32_t out_features, int32_t in_features,
+                                     void* workspace /*dev|NULL*/, size_t workspace_bytes, void* stream);
 
 /*
  * Column sum of a contiguous (rows x cols) matrix into float32 -- the bias gradient of a projection

@@ -88,3 +88,50 @@ def test_query_value_cast_is_the_stock_sequence():
         query_value_cast(torch.zeros(4, 8, device="cuda", dtype=torch.bfloat16), torch.zeros(4, 8, device="cuda"))
     with pytest.raises(RuntimeError):
         query_value_cast(torch.zeros(4, 8), torch.zeros(4, 8))
+
+
+@pytest.mark.parametrize("rows,out_f,in_f", [(1, 256, 256), (777, 1024, 256), (5000, 256, 1024), (21504, 192, 256), (33, 96, 256)])
+def test_f32_projection_on_tensor_cores_is_at_least_as_accurate_as_sgemm(rows, out_f, in_f, monkeypatch):
+    """float32 projections through cuBLASLt's emulated-float32 compute type (csrc/gemm_f32.cu): forward (bias, bias + ReLU)
+    and both backward products against float64, and never worse than twice the error of torch's own SGEMM path."""
+    from weed_instance_segmentation_b200 import linear as L
+    if not L.f32_gemm_available():
+        pytest.skip("the CUDA toolkit's cuBLASLt with float32 emulation is not available on this box")
+    g = torch.Generator(device="cuda").manual_seed(rows + out_f)
+    x = (2.0 * torch.randn(3, rows, in_f, device="cuda", generator=g)).requires_grad_(True)
+    w = (0.1 * torch.randn(out_f, in_f, device="cuda", generator=g)).requires_grad_(True)
+    b = (0.1 * torch.randn(out_f, device="cuda", generator=g)).requires_grad_(True)
+    go = torch.randn(3, rows, out_f, device="cuda", generator=g)
+
+    def run(fn):
+        for t in (x, w, b):
+            t.grad = None
+        y = fn(x, w, b)
+        y.backward(go)
+        return [y.detach(), x.grad.clone(), w.grad.clone(), b.grad.clone()]
+
+    xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    for relu in (False, True):
+        fn = L.linear_relu if relu else L.linear
+        got = run(fn)
+        monkeypatch.setattr(L, "_F32_EMULATED", False)
+        native = run(fn)  # torch's SGEMM through the same autograd functions
+        monkeypatch.setattr(L, "_F32_EMULATED", True)
+        for t in (xr, wr, br):
+            t.grad = None
+        yr = F.linear(xr, wr, br)
+        yr = F.relu(yr) if relu else yr
+        yr.backward(go.double())
+        want = [yr.detach(), xr.grad, wr.grad, br.grad]
+        for name, a, n, c in zip(("y", "grad_x", "grad_w", "grad_b"), got, native, want):
+            assert a.dtype == torch.float32 and a.shape == c.shape
+            if relu and name != "y":
+                continue  # a pre-activation within round-off of 0 may switch its mask between the two float32 paths
+            e, en = _rel(a, c), _rel(n, c)
+            assert e <= 2e-6, (relu, name, e)
+            assert e <= 2 * en + 1e-7, (relu, name, e, en)
+        if relu:  # gradients: compare where both float32 paths agree on the mask
+            same = ((got[0] > 0) == (native[0] > 0)).all()
+            if same:
+                for name, a, c in zip(("grad_x", "grad_w", "grad_b"), got[1:], want[1:]):
+                    assert _rel(a, c) <= 5e-6, (name, _rel(a, c))

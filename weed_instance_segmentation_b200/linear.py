@@ -7,12 +7,66 @@ encoder layer). Under autocast the inputs are cast to the autocast dtype exactly
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
 from . import _cabi
 
 _DTYPE_CODE = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16}
+
+# float32 projections on the bf16 tensor cores (csrc/gemm_f32.cu: cuBLASLt's CUBLAS_COMPUTE_32F_EMULATED_16BFX9, at least
+# SGEMM's accuracy at ~2x its speed). MSDA_B200_F32_GEMM=native keeps torch's SGEMM.
+_F32_EMULATED = os.environ.get("MSDA_B200_F32_GEMM", "emulated") != "native"
+_f32_ws: dict = {}
+_F32_WS_BYTES = 64 << 20
+
+
+def f32_gemm_available() -> bool:
+    """True when the CUDA toolkit's cuBLASLt (>= 12.9) could be opened and accepts the emulated float32 compute type."""
+    return bool(_F32_EMULATED and torch.cuda.is_available() and _cabi.load().msda_b200_linear_f32_available())
+
+
+def _use_f32_gemm(x, weight) -> bool:
+    return (_F32_EMULATED and x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32
+            and not torch.is_autocast_enabled("cuda") and x.numel() > 0 and f32_gemm_available())
+
+
+def _f32_workspace(device):
+    ws = _f32_ws.get(device)
+    if ws is None:
+        ws = _f32_ws[device] = torch.empty(_F32_WS_BYTES, dtype=torch.uint8, device=device)
+    return ws
+
+
+def _f32_forward(x2, weight, bias, relu):
+    lib = _cabi.load()
+    y = torch.empty((x2.shape[0], weight.shape[0]), dtype=torch.float32, device=x2.device)
+    ws = _f32_workspace(x2.device)
+    with torch.cuda.device(x2.device):
+        _cabi.check(lib.msda_b200_linear_f32_forward(x2.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                                     1 if relu else 0, y.data_ptr(), x2.shape[0], weight.shape[0], weight.shape[1],
+                                                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+    return y
+
+
+def _f32_backward(g2, x2, weight, need_x, need_w):
+    lib = _cabi.load()
+    ws = _f32_workspace(g2.device)
+    M, N, K = g2.shape[0], weight.shape[0], weight.shape[1]
+    gx = gw = None
+    with torch.cuda.device(g2.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if need_x:
+            gx = torch.empty((M, K), dtype=torch.float32, device=g2.device)
+            _cabi.check(lib.msda_b200_linear_f32_grad_input(g2.data_ptr(), weight.data_ptr(), gx.data_ptr(), M, N, K,
+                                                            ws.data_ptr(), ws.numel(), stream))
+        if need_w:
+            gw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
+            _cabi.check(lib.msda_b200_linear_f32_grad_weight(g2.data_ptr(), x2.data_ptr(), gw.data_ptr(), M, N, K,
+                                                             ws.data_ptr(), ws.numel(), stream))
+    return gx, gw
 
 
 def column_sum(matrix: torch.Tensor) -> torch.Tensor:
@@ -38,7 +92,12 @@ class LinearFunction(torch.autograd.Function):
                 y = F.linear(xc, wc, bc)
         else:
             xc, wc = x, weight
-            y = F.linear(x, weight, bias)
+            ctx.f32 = _use_f32_gemm(x, weight) and bias.dtype == torch.float32
+            if ctx.f32:
+                xc, wc = x.contiguous(), weight.contiguous()
+                y = _f32_forward(xc.reshape(-1, xc.shape[-1]), wc, bias.contiguous(), False).reshape(*xc.shape[:-1], wc.shape[0])
+            else:
+                y = F.linear(x, weight, bias)
         ctx.save_for_backward(xc, wc)
         ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype)
         return y
@@ -51,8 +110,12 @@ class LinearFunction(torch.autograd.Function):
         gy = grad_y.to(xc.dtype).contiguous()
         g2 = gy.reshape(-1, gy.shape[-1])
         need_x, need_w, need_b = ctx.needs_input_grad
-        grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
-        grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
+        if getattr(ctx, "f32", False):
+            grad_x, grad_w = _f32_backward(g2, xc.reshape(-1, xc.shape[-1]), wc, need_x, need_w)
+            grad_x = grad_x.reshape(xc.shape) if need_x else None
+        else:
+            grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
+            grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
         grad_b = column_sum(g2).to(bd) if need_b else None
         return grad_x, grad_w, grad_b
 
@@ -70,8 +133,13 @@ class LinearReLUFunction(torch.autograd.Function):
             xc, wc, bc = x.to(dt), weight.to(dt), bias.to(dt)
         else:
             xc, wc, bc = x, weight, bias
-        with torch.autocast("cuda", enabled=False):
-            y = torch._addmm_activation(bc, xc.reshape(-1, xc.shape[-1]), wc.t(), use_gelu=False)
+        ctx.f32 = (not torch.is_autocast_enabled("cuda")) and _use_f32_gemm(x, weight) and bias.dtype == torch.float32
+        if ctx.f32:
+            xc, wc = x.contiguous(), weight.contiguous()
+            y = _f32_forward(xc.reshape(-1, xc.shape[-1]), wc, bias.contiguous(), True)
+        else:
+            with torch.autocast("cuda", enabled=False):
+                y = torch._addmm_activation(bc, xc.reshape(-1, xc.shape[-1]), wc.t(), use_gelu=False)
         y = y.reshape(*xc.shape[:-1], wc.shape[0])
         ctx.save_for_backward(xc, wc, y)
         ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype)
@@ -85,8 +153,12 @@ class LinearReLUFunction(torch.autograd.Function):
         gy = torch.ops.aten.threshold_backward(grad_y.to(y.dtype).contiguous(), y, 0)  # relu'
         g2 = gy.reshape(-1, gy.shape[-1])
         need_x, need_w, need_b = ctx.needs_input_grad
-        grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
-        grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
+        if getattr(ctx, "f32", False):
+            grad_x, grad_w = _f32_backward(g2, xc.reshape(-1, xc.shape[-1]), wc, need_x, need_w)
+            grad_x = grad_x.reshape(xc.shape) if need_x else None
+        else:
+            grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
+            grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
         grad_b = column_sum(g2).to(bd) if need_b else None
         return grad_x, grad_w, grad_b
 
