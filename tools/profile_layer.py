@@ -23,8 +23,14 @@ mask = torch.zeros(B, S, dtype=torch.bool, device=dev)
 ref = synth.reference_points(SHAPES, device=dev)[None].expand(B, -1, -1, -1).contiguous()
 lsi = torch.tensor(synth.level_start_index(SHAPES), device=dev); go = torch.randn(B, S, 256, device=dev)
 
+AMP = os.environ.get("PROFILE_LAYER_AMP", "bf16") == "bf16"  # PROFILE_LAYER_AMP=none: the float32 layer
+
+
 def step():
-    with torch.autocast("cuda", dtype=torch.bfloat16):
+    x.grad = None
+    for p_ in layer.parameters():
+        p_.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=AMP):
         out = layer(x, mask, position_embeddings=pos, reference_points=ref, spatial_shapes_list=SHAPES, level_start_index=lsi)[0]
     out.backward(go.to(out.dtype))
 
