@@ -2,7 +2,7 @@
 # `ncu --set full` over one launch of every library kernel (tools/ncu_kernels.py) + a CSV summary of the metrics
 # profiles/ quotes.  Run on the GPU box: ./tools/ncu_all_kernels.sh <tag>
 TAG=${1:-r01_all_kernels}
-KERNELS=${2:-'msda_|point_sample|add_layernorm|colsum'}
+KERNELS=${2:-'msda_|point_sample|add_layernorm|colsum|qv_cast'}
 mkdir -p gpurun_out
 set -e
 timeout 600 python tools/ncu_kernels.py > gpurun_out/${TAG}_plain.log 2>&1 || { tail -5 gpurun_out/${TAG}_plain.log; exit 1; }

@@ -55,7 +55,15 @@ def main():
     y = layer_norm.add_layer_norm(x, r, w, b, 1e-5)
     y.backward(torch.randn_like(y))
     linear.column_sum(x.detach())
+    # the layer's closing clamp inside the LayerNorm kernels, and the attention module's bf16 operands from one kernel
+    yc = layer_norm.add_layer_norm(x, r, w, b, 1e-5, clamp=float(torch.finfo(torch.float32).max - 1000))
+    yc.backward(torch.randn_like(yc))
+    hq = torch.randn(B * S, 256, device=dev, generator=g).requires_grad_(True)
+    pq = torch.randn(B * S, 256, device=dev, generator=g).requires_grad_(True)
+    qb, vb = linear.query_value_cast(hq, pq)
+    torch.autograd.backward([qb, vb], [torch.randn_like(qb), torch.randn_like(vb)])
     torch.cuda.synchronize()
+    del yc, hq, pq, qb, vb
     del x, r, y
     torch.cuda.empty_cache()
     # 6. loss / matcher path at the config-4 loss geometry
