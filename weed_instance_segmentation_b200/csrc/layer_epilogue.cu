@@ -214,26 +214,32 @@ int launch_bwd_ch(int xd, int rd, const float* dy, const void* dy_lowp, const vo
                   const float* mean,
                   const float* rstd, float* ds, void* ds_lowp, float* dgamma, float* dbeta, long long N,
                   const float* beta, float clamp, cudaStream_t st) {
-  // ~4 blocks per SM; each block walks a contiguous range of rows so the gamma/beta partials stay in registers
-  long long blocks = 148 * 4;
-  if (blocks > (N + kRowsPerBlock - 1) / kRowsPerBlock) blocks = (N + kRowsPerBlock - 1) / kRowsPerBlock;
-  const int rows_per_block = (int)((N + blocks - 1) / blocks);
-  blocks = (N + rows_per_block - 1) / rows_per_block;
+  // Exactly ONE wave of resident blocks: 148 SMs x what the kernel's register count lets an SM hold (3 at 80 registers).
+  // The former fixed 148 x 4 ran as 1.33 waves -- a third of the time on a quarter-full GPU (ncu r02: dram 50 %).
+  // Each block walks a contiguous range of rows so the gamma / beta partials stay in registers.
   using bf = __nv_bfloat16;
-#define MSDA_LN_BWD(XT, RT)                                                                                       \
+#define MSDA_LN_BWD_LAUNCH(KERN)                                                                                  \
   do {                                                                                                            \
-    if (ds_lowp)                                                                                                  \
-      add_layernorm_bwd_kernel<XT, RT, CH, true><<<(unsigned)blocks, kThreads, 0, st>>>(                          \
-          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block, beta, clamp);                   \
-    else                                                                                                          \
-      add_layernorm_bwd_kernel<XT, RT, CH, false><<<(unsigned)blocks, kThreads, 0, st>>>(                         \
-          dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, rows_per_block, beta, clamp);                   \
+    int occ = 0;                                                                                                  \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERN, kThreads, 0) != cudaSuccess || occ < 1) occ = 3; \
+    long long blocks = 148LL * occ;                                                                               \
+    if (blocks > (N + kRowsPerBlock - 1) / kRowsPerBlock) blocks = (N + kRowsPerBlock - 1) / kRowsPerBlock;       \
+    const int rows_per_block = (int)((N + blocks - 1) / blocks);                                                  \
+    blocks = (N + rows_per_block - 1) / rows_per_block;                                                           \
+    KERN<<<(unsigned)blocks, kThreads, 0, st>>>(dy, dy_lowp, x, r, gamma, mean, rstd, ds, ds_lowp, dgamma, dbeta, N, \
+                                                rows_per_block, beta, clamp);                                     \
+  } while (0)
+#define MSDA_LN_BWD(XT, RT)                                                              \
+  do {                                                                                   \
+    if (ds_lowp) MSDA_LN_BWD_LAUNCH((add_layernorm_bwd_kernel<XT, RT, CH, true>));       \
+    else MSDA_LN_BWD_LAUNCH((add_layernorm_bwd_kernel<XT, RT, CH, false>));              \
   } while (0)
   if (xd == MSDA_B200_BF16 && rd == MSDA_B200_F32) MSDA_LN_BWD(bf, float);
   else if (xd == MSDA_B200_F32 && rd == MSDA_B200_F32) MSDA_LN_BWD(float, float);
   else if (xd == MSDA_B200_BF16 && rd == MSDA_B200_BF16) MSDA_LN_BWD(bf, bf);
   else MSDA_LN_BWD(float, bf);
 #undef MSDA_LN_BWD
+#undef MSDA_LN_BWD_LAUNCH
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
 }
