@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define MSDA_B200_ABI_VERSION 10
+#define MSDA_B200_ABI_VERSION 11
 #define MSDA_B200_MAX_LEVELS 8
 
 /* dtype codes */
@@ -244,6 +244,15 @@ int msda_b200_linear_f32_grad_weight(const float* grad_y /*dev*/, const float* x
  */
 int msda_b200_column_sum(const void* matrix /*dev*/, int dtype, float* out /*dev, cols*/, int64_t rows, int32_t cols,
                          void* stream);
+
+/*
+ * The FFN's ReLU backward and fc1's bias gradient (M2F:1052-1053) in one pass: grad_masked = grad_y where y > 0 else 0
+ * (aten threshold_backward with the saved activation y = relu(z)), column_sum = sum over rows of grad_masked (float32,
+ * zero-filled by the library first).  grad_y, y, grad_masked: contiguous (rows x cols), all of `dtype`; cols as above.
+ */
+int msda_b200_relu_backward_column_sum(const void* grad_y /*dev*/, const void* y /*dev*/, int dtype,
+                                       void* grad_masked /*dev*/, float* column_sum /*dev, cols*/, int64_t rows,
+                                       int32_t cols, void* stream);
 
 /*
  * Batched bilinear point sampling -- the `sample_point` primitive of the loss / matcher path

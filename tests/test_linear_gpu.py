@@ -135,3 +135,20 @@ def test_f32_projection_on_tensor_cores_is_at_least_as_accurate_as_sgemm(rows, o
             if same:
                 for name, a, c in zip(("grad_x", "grad_w", "grad_b"), got[1:], want[1:]):
                     assert _rel(a, c) <= 5e-6, (name, _rel(a, c))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols", [(1, 8), (37, 1024), (5000, 256), (0, 64)])
+def test_relu_backward_column_sum_matches_torch(rows, cols, dtype):
+    """ReLU backward mask and the bias gradient from one kernel: the masked gradient is bit-identical to aten
+    threshold_backward, the column sum matches its float64 sum."""
+    from weed_instance_segmentation_b200.linear import relu_backward_column_sum
+    g = torch.Generator(device="cuda").manual_seed(rows + cols)
+    y = torch.relu(torch.randn(rows, cols, device="cuda", generator=g)).to(dtype)
+    gy = torch.randn(rows, cols, device="cuda", generator=g).to(dtype)
+    got, col = relu_backward_column_sum(gy, y)
+    want = torch.ops.aten.threshold_backward(gy, y, 0)
+    assert got.dtype == dtype and torch.equal(got, want)
+    ref = want.double().sum(0)
+    assert col.dtype == torch.float32 and col.shape == (cols,)
+    assert (col.double() - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0) + 1e-6 * max(rows, 1) ** 0.5

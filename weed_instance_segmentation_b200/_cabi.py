@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libmsda_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_LEVELS = 8
 F32, BF16, U8 = 0, 1, 2
 FLAG_PROFILE = 1
@@ -37,6 +37,7 @@ EXPORTS = (
     "msda_b200_add_layernorm_clamp_backward",
     "msda_b200_query_value_cast_forward",
     "msda_b200_query_value_cast_backward",
+    "msda_b200_relu_backward_column_sum",
     "msda_b200_linear_f32_available",
     "msda_b200_linear_f32_forward",
     "msda_b200_linear_f32_grad_input",
@@ -132,6 +133,8 @@ def load() -> ctypes.CDLL:
     for fn in (lib.msda_b200_linear_f32_grad_input, lib.msda_b200_linear_f32_grad_weight):
         fn.restype = ctypes.c_int
         fn.argtypes = [vp, vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_size_t, vp]
+    lib.msda_b200_relu_backward_column_sum.restype = ctypes.c_int
+    lib.msda_b200_relu_backward_column_sum.argtypes = [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_column_sum.restype = ctypes.c_int
     lib.msda_b200_column_sum.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int64, ctypes.c_int32, vp]
     lib.msda_b200_groupnorm_to_rows_forward.restype = ctypes.c_int

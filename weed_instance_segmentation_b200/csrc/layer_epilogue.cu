@@ -349,6 +349,9 @@ struct ColVec<float> {
     const float4 v = __ldg(reinterpret_cast<const float4*>(base) + idx);
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
   }
+  static __device__ __forceinline__ void store(void* base, long long idx, const float (&f)[4]) {
+    reinterpret_cast<float4*>(base)[idx] = make_float4(f[0], f[1], f[2], f[3]);
+  }
 };
 template <>
 struct ColVec<__nv_bfloat16> {
@@ -360,12 +363,25 @@ struct ColVec<__nv_bfloat16> {
     f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
     f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
   }
+  // exact for values that came out of load() (bfloat16-representable): the low 16 bits are zero
+  static __device__ __forceinline__ void store(void* base, long long idx, const float (&f)[8]) {
+    uint4 v;
+    v.x = (__float_as_uint(f[0]) >> 16) | (__float_as_uint(f[1]) & 0xffff0000u);
+    v.y = (__float_as_uint(f[2]) >> 16) | (__float_as_uint(f[3]) & 0xffff0000u);
+    v.z = (__float_as_uint(f[4]) >> 16) | (__float_as_uint(f[5]) & 0xffff0000u);
+    v.w = (__float_as_uint(f[6]) >> 16) | (__float_as_uint(f[7]) & 0xffff0000u);
+    reinterpret_cast<uint4*>(base)[idx] = v;
+  }
 };
 
 // block = (cv column vectors) x (rl row lanes); every thread walks rows r0 + ry, r0 + ry + rl, ...
-template <typename T>
+// RELU: m is the gradient that arrived at relu(z), y = relu(z) the saved activation; the kernel also writes the masked
+// gradient (aten threshold_backward: grad where y > 0, else 0) to gm -- the FFN's ReLU backward and the bias gradient of
+// fc1 (M2F:1052-1053) in one pass over the (rows x 1024) matrix instead of a mask kernel and a second read.
+template <typename T, bool RELU>
 __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ m, float* __restrict__ out, long long rows,
-                                                     int cv /* cols / N */, int rl, int rows_per_block) {
+                                                     int cv /* cols / N */, int rl, int rows_per_block,
+                                                     const void* __restrict__ y = nullptr, void* __restrict__ gm = nullptr) {
   constexpr int N = ColVec<T>::N;
   extern __shared__ float s_part[];  // [rl][cv * N]
   const int cx = threadIdx.x % cv, ry = threadIdx.x / cv;
@@ -378,6 +394,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ m,
     for (long long r = r0 + ry; r < r1; r += rl) {
       float f[N];
       ColVec<T>::load(m, r * cv + cx, f);
+      if (RELU) {
+        float a[N];
+        ColVec<T>::load(y, r * cv + cx, a);
+#pragma unroll
+        for (int j = 0; j < N; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
+        ColVec<T>::store(gm, r * cv + cx, f);
+      }
 #pragma unroll
       for (int j = 0; j < N; ++j) acc[j] += f[j];
     }
@@ -394,7 +417,22 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ m,
 
 }  // namespace
 
+static int column_sum_impl(const void* matrix, int dtype, float* out, int64_t rows, int32_t cols, const void* y, void* gm,
+                           void* stream);
+
 extern "C" int msda_b200_column_sum(const void* matrix, int dtype, float* out, int64_t rows, int32_t cols, void* stream) {
+  return column_sum_impl(matrix, dtype, out, rows, cols, nullptr, nullptr, stream);
+}
+
+extern "C" int msda_b200_relu_backward_column_sum(const void* grad_y, const void* y, int dtype, void* grad_masked,
+                                                  float* column_sum, int64_t rows, int32_t cols, void* stream) {
+  if (rows > 0 && (!y || !grad_masked))
+    return msda_b200_internal_fail(MSDA_B200_ERR_INVALID, "relu_backward_column_sum: NULL tensor pointer");
+  return column_sum_impl(grad_y, dtype, column_sum, rows, cols, y ? y : grad_y, grad_masked ? grad_masked : (void*)1, stream);
+}
+
+static int column_sum_impl(const void* matrix, int dtype, float* out, int64_t rows, int32_t cols, const void* y, void* gm,
+                           void* stream) {
   if (bad_dtype(dtype)) return msda_b200_internal_fail(MSDA_B200_ERR_UNSUPPORTED, "column_sum: dtype must be 0 (f32) or 1 (bf16)");
   const int n = dtype == MSDA_B200_BF16 ? 8 : 4;
   if (rows < 0 || cols <= 0 || cols % n != 0 || cols > 2048)
@@ -416,10 +454,15 @@ extern "C" int msda_b200_column_sum(const void* matrix, int dtype, float* out, i
   const int rows_per_block = (int)((rows + blocks - 1) / blocks);
   blocks = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = sizeof(float) * (size_t)rl * cols;
-  if (dtype == MSDA_B200_BF16)
-    colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
+  if (gm) {
+    if (dtype == MSDA_B200_BF16)
+      colsum_kernel<__nv_bfloat16, true><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block, y, gm);
+    else
+      colsum_kernel<float, true><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block, y, gm);
+  } else if (dtype == MSDA_B200_BF16)
+    colsum_kernel<__nv_bfloat16, false><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
   else
-    colsum_kernel<float><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
+    colsum_kernel<float, false><<<(unsigned)blocks, threads, smem, st>>>(matrix, out, rows, cv, rl, rows_per_block);
   const cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? MSDA_B200_OK : msda_b200_internal_fail(MSDA_B200_ERR_CUDA, cudaGetErrorString(e));
 }

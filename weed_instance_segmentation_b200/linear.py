@@ -81,6 +81,22 @@ def column_sum(matrix: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def relu_backward_column_sum(grad_y: torch.Tensor, y: torch.Tensor):
+    """``(threshold_backward(grad_y, y, 0), its sum over rows in float32)`` from one kernel: the FFN's ReLU backward and
+    fc1's bias gradient. ``grad_y`` and ``y``: same shape / dtype (float32 or bfloat16), CUDA."""
+    lib = _cabi.load()
+    C = y.shape[-1]
+    g, a = grad_y.contiguous(), y.contiguous()
+    out = torch.empty_like(g)
+    col = torch.empty(C, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _cabi.check(lib.msda_b200_relu_backward_column_sum(g.data_ptr() if g.numel() else None, a.data_ptr() if a.numel() else None,
+                                                           _DTYPE_CODE[g.dtype], out.data_ptr() if out.numel() else None,
+                                                           col.data_ptr(), g.numel() // C, C,
+                                                           torch.cuda.current_stream().cuda_stream))
+    return out, col
+
+
 class LinearFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
@@ -150,7 +166,8 @@ class LinearReLUFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         xc, wc, y = ctx.saved_tensors
         xd, wd, bd = ctx.in_dtypes
-        gy = torch.ops.aten.threshold_backward(grad_y.to(y.dtype).contiguous(), y, 0)  # relu'
+        # relu' and the bias gradient (the column sum of the masked gradient) from one pass over the matrix
+        gy, col = relu_backward_column_sum(grad_y.to(y.dtype), y)
         g2 = gy.reshape(-1, gy.shape[-1])
         need_x, need_w, need_b = ctx.needs_input_grad
         if getattr(ctx, "f32", False):
@@ -159,7 +176,7 @@ class LinearReLUFunction(torch.autograd.Function):
         else:
             grad_x = (g2 @ wc).reshape(xc.shape).to(xd) if need_x else None
             grad_w = (g2.t() @ xc.reshape(-1, xc.shape[-1])).to(wd) if need_w else None
-        grad_b = column_sum(g2).to(bd) if need_b else None
+        grad_b = col.to(bd) if need_b else None
         return grad_x, grad_w, grad_b
 
 
