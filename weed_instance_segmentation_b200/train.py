@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 from . import hf_patch, modules, synth
+from .linear import f32_gemm_available as _f32_gemm_available
 
 # /root/reference/config.py:5-8
 LEARNING_RATE = 5e-5
@@ -251,6 +252,10 @@ def bench_block(device, world: int, rank: int, batch: int = 16, height: int = 96
         # one bucketed all-reduce of every gradient per optimizer step (every GRADIENT_ACCUMULATION micro-batches)
         "allreduce_bytes": nparam * 4 if world > 1 else 0, "allreduce_every_micro_batches": GRADIENT_ACCUMULATION,
         "params": nparam, "backend": "nccl" if world > 1 else None,
+        # which GEMM the encoder layers' float32 projections ran on (csrc/gemm_f32.cu; falls back when the toolkit's
+        # cuBLASLt >= 12.9 cannot be opened)
+        "f32_projections": ("cuBLASLt CUBLAS_COMPUTE_32F_EMULATED_16BFX9 (bf16 tensor cores)" if _f32_gemm_available()
+                            else "torch SGEMM"),
     }
     if with_stock and world == 1:
         s2, l2, _ = run("reference", steps, 3)
