@@ -60,7 +60,7 @@ def test_round2_lines():
     assert t1["n_gpus"] == 1 and t1["allreduce_bytes"] == 0 and t1["stock_hf"]["images_per_s"] > 0
     r = _line("r02_bench_reference_arm.json")
     assert r["impl"] == "reference" and r["metric"] == d["metric"] and r["config"]["workload"] == d["config"]["workload"]
-    for n in (2, 8):
+    for n in (2, 4, 8):
         m = _line(f"r02_bench_n{n}.json")
         t = m["train"]
         assert m["n_gpus"] == n and t["n_gpus"] == n and t["backend"] == "nccl"
